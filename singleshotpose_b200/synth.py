@@ -1,0 +1,72 @@
+"""Seeded synthetic inputs for tests, smoke and bench: uniform RGB batches,
+one-ground-truth label rows in the reference's 50x21 layout (dataset.py:107 / region_loss.py:29-36),
+box-corner 3-D models and exact/noisy 2-D projections for PnP."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .cfgs import LINEMOD_INTRINSICS
+
+
+def images(batch, height=416, width=416, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(batch, 3, height, width, generator=g)
+
+
+def targets(batch, seed=1, num_keypoints=9, max_objs=50):
+    """(batch, 50*21) float32: one object per image, class 0, centroid U(.1,.9), 8 corners =
+    centroid + U(-.15,.15), then x/y range; remaining slots zero."""
+    rng = np.random.default_rng(seed)
+    nl = 2 * num_keypoints + 3
+    t = np.zeros((batch, max_objs * nl), np.float32)
+    for b in range(batch):
+        c = rng.uniform(0.1, 0.9, size=2)
+        pts = np.concatenate([c[None], c[None] + rng.uniform(-0.15, 0.15, size=(num_keypoints - 1, 2))])
+        t[b, 0] = 0
+        t[b, 1:1 + 2 * num_keypoints] = pts.reshape(-1)
+        t[b, 1 + 2 * num_keypoints] = pts[:, 0].max() - pts[:, 0].min()
+        t[b, 2 + 2 * num_keypoints] = pts[:, 1].max() - pts[:, 1].min()
+    return torch.from_numpy(t)
+
+
+def intrinsics(dtype=np.float64):
+    k = LINEMOD_INTRINSICS
+    return np.array([[k["fx"], 0.0, k["u0"]], [0.0, k["fy"], k["v0"]], [0.0, 0.0, 1.0]], dtype)
+
+
+def box_points(half_extents=(0.038, 0.039, 0.046), with_center=True):
+    """(9,3) or (8,3) float32: origin + the 8 corners in get_3D_corners order (utils.py:66-84:
+    x outermost, z fastest, min before max)."""
+    hx, hy, hz = half_extents
+    c = np.array([[sx * hx, sy * hy, sz * hz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)])
+    if with_center:
+        c = np.concatenate([np.zeros((1, 3)), c])
+    return c.astype(np.float32)
+
+
+def _rodrigues(r):
+    th = np.linalg.norm(r, axis=-1, keepdims=True)
+    u = r / np.maximum(th, 1e-300)
+    c, s = np.cos(th)[..., None], np.sin(th)[..., None]
+    ux = np.zeros(r.shape[:-1] + (3, 3))
+    ux[..., 0, 1], ux[..., 0, 2] = -u[..., 2], u[..., 1]
+    ux[..., 1, 0], ux[..., 1, 2] = u[..., 2], -u[..., 0]
+    ux[..., 2, 0], ux[..., 2, 1] = -u[..., 1], u[..., 0]
+    return c * np.eye(3) + (1 - c) * u[..., :, None] * u[..., None, :] + s * ux
+
+
+def pnp_problems(n, sigma=0.5, seed=5, with_center=True):
+    """n synthetic PnP problems sharing one 3-D model and K.  Returns dict with P3 (N,3) f32,
+    uv (n,N,2) f32, K (3,3) f32, and the generating R (n,3,3), t (n,3) in f64."""
+    rng = np.random.default_rng(seed)
+    P3 = box_points(with_center=with_center)
+    K = intrinsics()
+    ax = rng.normal(size=(n, 3)); ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+    rv = ax * rng.uniform(0, np.pi, size=(n, 1))
+    t = np.stack([rng.uniform(-.2, .2, n), rng.uniform(-.15, .15, n), rng.uniform(.6, 1.2, n)], 1)
+    R = _rodrigues(rv)
+    Pc = np.einsum("nij,kj->nki", R, P3.astype(np.float64)) + t[:, None, :]
+    uv = np.stack([K[0, 0] * Pc[..., 0] / Pc[..., 2] + K[0, 2], K[1, 1] * Pc[..., 1] / Pc[..., 2] + K[1, 2]], -1)
+    uv = uv + rng.normal(size=uv.shape) * sigma
+    return dict(P3=P3, uv=uv.astype(np.float32), K=K.astype(np.float32), R=R, t=t)

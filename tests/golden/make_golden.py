@@ -1,0 +1,179 @@
+"""Generate the golden fixtures under tests/golden/ from the REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference and cv2):
+    python tests/golden/make_golden.py
+It (1) checks that the oracle restatements agree with the reference's own functions on the
+same seeded inputs, and (2) stores the reference outputs as small .npz files so that
+tests/test_oracle.py can re-pin the oracle -- and tests/test_*_gpu.py the CUDA path --
+on machines where /root/reference does not exist.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, REPO)
+
+from oracle.darknet_ref import RefDarknet                      # noqa: E402
+from oracle import region_loss_ref as RL                       # noqa: E402
+from oracle.decode_ref import get_region_boxes_ref             # noqa: E402
+from oracle.pnp_ref import pnp_ref                             # noqa: E402
+from singleshotpose_b200 import synth                          # noqa: E402
+from singleshotpose_b200.cfgs import write_cfg                 # noqa: E402
+
+
+def ref_import():
+    sys.path.insert(0, REF)
+    cwd = os.getcwd()
+    os.chdir(REF)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import darknet as ref_darknet
+        import region_loss as ref_rl
+        import utils as ref_utils
+    os.chdir(cwd)
+    return ref_darknet, ref_rl, ref_utils
+
+
+def populate_and_eval(model, x):
+    """Shared recipe (also used by the tests on the oracle model)."""
+    bns = [m for m in model.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    for bn in bns:
+        bn.reset_running_stats(); bn.momentum = None
+    model.train()
+    with torch.no_grad():
+        for s in (0, 10, 11):
+            model(synth.images(2, seed=s))
+        model.eval()
+        out = model(x).numpy().copy()
+    for bn in bns:
+        bn.momentum = 0.1
+    model.train()
+    return out
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    ref_darknet, ref_rl, ref_utils = ref_import()
+
+    # ---------------- network forward / backward ----------------
+    torch.manual_seed(0)
+    ref_model = ref_darknet.Darknet(os.path.join(REF, "cfg/yolo-pose.cfg"))
+    torch.manual_seed(0)
+    ora_model = RefDarknet(write_cfg())
+    sd_ref, sd_ora = ref_model.state_dict(), ora_model.state_dict()
+    assert list(sd_ref.keys()) == list(sd_ora.keys()), "state_dict key order differs"
+    for k in sd_ref:
+        assert torch.equal(sd_ref[k], sd_ora[k]), k
+    print("seeded init identical for %d tensors" % len(sd_ref))
+
+    x = synth.images(2, seed=0)
+    tgt = synth.targets(2, seed=1)
+    ref_model.train(); ora_model.train()
+    out_ref = ref_model(x)
+    out_ora = ora_model(x)
+    assert torch.equal(out_ref, out_ora), (out_ref - out_ora).abs().max()
+    # loss + backward through the reference network with the restated loss head
+    loss, info = RL.region_loss_ref(out_ref, tgt, 20, build_targets=lambda *a: ref_rl.build_targets(*a, 0))
+    loss.backward()
+    gnorm = np.array([p.grad.double().norm().item() for p in ref_model.parameters()])
+    gsum = np.array([p.grad.double().sum().item() for p in ref_model.parameters()])
+    names = [n for n, _ in ref_model.named_parameters()]
+    first_w_grad = ref_model.models[0][0].weight.grad.numpy().copy()
+    last_w_grad = ref_model.models[30][0].weight.grad.numpy().copy()
+    train_logits = out_ref.detach().numpy().copy()
+    # running-stat update rule (momentum 0.1, unbiased variance) after ONE train forward
+    rm = ref_model.models[0][1].running_mean.numpy().copy()
+    rv = ref_model.models[29][1].running_var.numpy().copy()
+    # populate running stats with the cumulative average of 3 train forwards (momentum=None) so that the
+    # eval-mode logits are O(1) (pristine (0,1) stats make eval output ~= the last bias)
+    eval_logits = populate_and_eval(ref_model, x)
+    assert torch.equal(torch.from_numpy(eval_logits), torch.from_numpy(populate_and_eval(ora_model, x)))
+    np.savez_compressed(os.path.join(HERE, "net_b2.npz"), train_logits=train_logits, eval_logits=eval_logits,
+                        loss=float(loss), grad_norms=gnorm, grad_sums=gsum, names=np.array(names),
+                        first_w_grad=first_w_grad, last_w_grad=last_w_grad[:, :64],
+                        running_mean0=rm, running_var29=rv)
+    print("net golden: train absmax %.4f eval absmax %.4f loss %.6f" % (
+        np.abs(train_logits).max(), np.abs(eval_logits).max(), float(loss)))
+
+    # ---------------- region loss head ----------------
+    g = torch.Generator().manual_seed(3)
+    B = 6
+    out = torch.randn(B, 20, 13, 13, generator=g) * 0.7
+    tgt = synth.targets(B, seed=4)
+    # make image 0's prediction good at the GT cell so tconf > 0, nCorrect > 0 and some conf_mask zeros exist
+    t0 = tgt[0].numpy()
+    gi, gj = int(t0[1] * 13), int(t0[2] * 13)
+    for k in range(9):
+        vx, vy = t0[1 + 2 * k] * 13 - gi, t0[2 + 2 * k] * 13 - gj
+        if k == 0:
+            vx, vy = np.log(vx / (1 - vx)), np.log(vy / (1 - vy))
+        out[0, 2 * k, gj, gi] = float(vx); out[0, 2 * k + 1, gj, gi] = float(vy)
+    res = {}
+    for epoch in (0, 20):
+        o = out.clone().requires_grad_(True)
+        loss, info = RL.region_loss_ref(o, tgt, epoch, build_targets=lambda *a: ref_rl.build_targets(*a, 0))
+        loss.backward()
+        o2 = out.clone().requires_grad_(True)
+        loss2, info2 = RL.region_loss_ref(o2, tgt, epoch)
+        loss2.backward()
+        assert torch.equal(loss, loss2) and torch.equal(o.grad, o2.grad), "restated build_targets differs"
+        for k in ("tconf", "conf_mask", "coord_mask"):
+            assert torch.equal(info[k], info2[k]), k
+        assert (info["nGT"], info["nCorrect"]) == (info2["nGT"], info2["nCorrect"])
+        res["loss_e%d" % epoch] = float(loss)
+        res["grad_e%d" % epoch] = o.grad.numpy().copy()
+        res["parts_e%d" % epoch] = np.array([float(info["loss_x"]), float(info["loss_y"]), float(info["loss_conf"])])
+        res["counters_e%d" % epoch] = np.array([info["nGT"], info["nCorrect"], info["nProposals"]])
+        if epoch == 20:
+            res["tconf"] = info["tconf"].numpy().copy(); res["conf_mask_sqrt"] = info["conf_mask"].numpy().copy()
+    # corner_confidence(s) direct pin
+    pc = torch.rand(18, 169, generator=g); gt = torch.rand(18, 1, generator=g).repeat(1, 169)
+    a = ref_utils.corner_confidences(pc.clone(), gt.clone()); b = RL.corner_confidences_ref(pc, gt)
+    assert torch.equal(a, b)
+    a1 = ref_utils.corner_confidence(list(gt[:, 0]), pc[:, 5].clone()); b1 = RL.corner_confidence_ref(list(gt[:, 0]), pc[:, 5])
+    assert torch.equal(a1, b1)
+    np.savez_compressed(os.path.join(HERE, "region_loss.npz"), output=out.numpy(), target=tgt.numpy(), **res)
+    print("region golden:", {k: v for k, v in res.items() if k.startswith(("loss", "counters"))})
+
+    # ---------------- decode (get_region_boxes): reference needs .cuda(); patch Tensor.cuda to identity ----
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            box_ref = ref_utils.get_region_boxes(out.clone(), 1, 9)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    box_ora = get_region_boxes_ref(out.clone(), 1, 9)
+    br = np.array([float(v) for v in box_ref]); bo = np.array([float(v) for v in box_ora])
+    assert np.array_equal(br, bo), (br, bo)
+    np.savez_compressed(os.path.join(HERE, "decode.npz"), output=out.numpy(), box=br)
+    print("decode golden box conf %.4f" % br[18])
+
+    # ---------------- PnP: reference utils.pnp (cv2) ----------------
+    res = {}
+    for sigma, tag in ((0.0, "s0"), (1.0, "s1")):
+        pr = synth.pnp_problems(64, sigma=sigma, seed=7)
+        Rs, ts = [], []
+        worst = 0.0
+        for i in range(64):
+            R, t = ref_utils.pnp(pr["P3"], pr["uv"][i], pr["K"])
+            Ro, to = pnp_ref(pr["P3"], pr["uv"][i], pr["K"])
+            ang = np.degrees(np.arccos(np.clip((np.trace(R @ Ro.T) - 1) / 2, -1, 1)))
+            worst = max(worst, ang, np.abs(t - to).max() * 1000)
+            Rs.append(R); ts.append(t.reshape(3))
+        assert worst < 1e-4, worst
+        res["uv_" + tag] = pr["uv"]; res["R_" + tag] = np.array(Rs); res["t_" + tag] = np.array(ts)
+        print("pnp golden sigma=%g: oracle vs cv2 worst (deg|mm) %.2e" % (sigma, worst))
+    np.savez_compressed(os.path.join(HERE, "pnp.npz"), P3=pr["P3"], K=pr["K"], **res)
+
+
+if __name__ == "__main__":
+    main()
