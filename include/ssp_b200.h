@@ -1,0 +1,113 @@
+/* ssp_b200.h -- C ABI of libssp_b200.so: the sm_100a kernels behind the singleshotpose hot path.
+ *
+ * The reference (microsoft/singleshotpose) has no FFI: its hot path is the Python surface
+ * Darknet.forward / RegionLoss.forward / get_region_boxes / pnp.  Each entry point below names the
+ * reference code it replaces (file:line under /root/reference); singleshotpose_b200/*.py are the
+ * thin Python mirrors of that surface that bind these symbols with ctypes.
+ *
+ * Conventions: plain pointers and sizes only; every pointer is a DEVICE pointer unless stated; all
+ * functions are asynchronous on `stream` (a cudaStream_t passed as void*), never allocate, never
+ * synchronise, and return 0 on success or a negative SSP_ERR_* code (ssp_last_error() gives the text).
+ * Thread-compatible: distinct host threads may call concurrently on distinct streams.
+ *
+ * Activation layout ("padded-flat NHWC"): a (N,C,H,W) feature map is a row-major matrix [rows][ld] with
+ *   row(n,h,w) = n*(H+1)*(W+1) + (h+1)*(W+1) + (w+1)
+ * (one shared zero pad pixel per image row, one shared zero pad row per image); buffers hold
+ * ssp_flat_alloc_rows(N,H,W) rows and must be zero-initialised once: kernels only ever write valid rows
+ * of operand planes, the zero pads are what makes a 3x3 tap a constant row shift.
+ * 16-bit operand planes come as fp16 "hi" (+ optional fp16 "lo", value = hi + lo) -- see DESIGN.md numerics.
+ */
+#ifndef SSP_B200_H
+#define SSP_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSP_OK 0
+#define SSP_ERR_ARG (-1)
+#define SSP_ERR_CUDA (-2)
+#define SSP_ERR_DRIVER (-3)
+
+#define SSP_FMT_F16 0
+#define SSP_FMT_BF16 1
+#define SSP_IMPL_TC 0    /* tcgen05 tensor-core kernel */
+#define SSP_IMPL_SIMT 1  /* fp32 CUDA-core kernel (cross-check / bring-up) */
+#define SSP_EPI_F32 0    /* store fp32 */
+#define SSP_EPI_STATS 1  /* store fp32 + per-channel sum / sum of squares over valid pixels (fp64) */
+#define SSP_EPI_BIAS 2   /* add bias, store fp32 */
+#define SSP_ROUTE_NONE 0
+#define SSP_ROUTE_DIRECT 1 /* consumer has the same geometry */
+#define SSP_ROUTE_POOL 2   /* consumer is behind MaxPool2d(2,2)          (darknet.py:168-176) */
+#define SSP_ROUTE_REORG 3  /* consumer is behind Reorg(2), marvis order  (darknet.py:16-35)   */
+
+int ssp_version(void);
+const char* ssp_last_error(void);              /* host pointer, thread-local text of the last failure */
+long long ssp_flat_alloc_rows(int N, int H, int W);
+long long ssp_flat_row(int n, int h, int w, int H, int W);
+
+/* ---- layout: train.py:83 `data.cuda()` hands NCHW fp32; the conv stack runs on padded-flat rows ---- */
+int ssp_pack_input_im2col(const float* x_nchw, void* hi, void* lo, int N, int H, int W, void* stream);
+int ssp_pack_nchw(const float* x_nchw, void* hi, void* lo_or_null, int N, int C, int H, int W, int ld, int c0,
+                  int fmt, float scale, void* stream);
+int ssp_unpack_nchw(const float* y_flat, float* out_nchw, int N, int C, int H, int W, int ld, int c0, void* stream);
+int ssp_unpack16_nchw(const void* hi, const void* lo_or_null, float* out_nchw, int N, int C, int H, int W, int ld,
+                      int c0, int fmt, void* stream);
+
+/* ---- nn.Conv2d forward and data gradient (darknet.py:156-160; autograd of train.py:103) ----
+ * out[m][n] = sum_tap sum_c A[m + shift(tap)][c] * B[n][tap*cin + c],  taps in {1, 9} (3x3 pad 1 / 1x1). */
+int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo_or_null, long long a_rows, int a_ld, int cin,
+                  const void* b_hi, const void* b_lo_or_null, int b_rows, int b_ld, int a_fmt, int b_fmt,
+                  int N, int H, int W, int taps, int cout, float* out, int out_ld, long long out_rows, int epi,
+                  const float* bias, double* stat_sum, double* stat_sq, void* stream);
+/* ---- nn.Conv2d weight gradient: dW[co][tap][ci] += scale * sum_m dY[m][co] * X[m + shift(tap)][ci] ---- */
+int ssp_wgrad_gemm(int impl, const void* dy, long long dy_rows, int dy_ld, int cout, int dy_fmt, const void* x,
+                   long long x_rows, int x_ld, int cin, int x_fmt, int N, int H, int W, int taps, float* dw,
+                   int dw_ld, int cin_store, float scale, void* stream);
+
+/* ---- nn.BatchNorm2d(eps=1e-4) + nn.LeakyReLU(0.1) + MaxPool2d/Reorg/route placement (darknet.py:96-106,157-176) ---- */
+int ssp_bn_finalize(double* stat_sum, double* stat_sq, double count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps, int train, float* mean,
+                    float* invstd, float* scale, float* shift, int C, void* stream);
+int ssp_bn_apply(const float* y, int y_ld, const float* scale, const float* shift, int N, int C, int H, int W,
+                 float slope, void* d0_hi, void* d0_lo, int d0_ld, int d0_c0, int d0_route, void* d1_hi, void* d1_lo,
+                 int d1_ld, int d1_c0, int d1_route, void* stream);
+int ssp_bn_bwd_reduce(const float* y, int y_ld, const float* scale, const float* shift, const float* mean,
+                      const float* invstd, const float* gamma, int N, int C, int H, int W, float slope,
+                      const float* g0, int g0_ld, int g0_c0, int g0_route, const float* g1, int g1_ld, int g1_c0,
+                      int g1_route, double* s1, double* s2, void* stream);
+int ssp_bn_bwd_apply(const float* y, int y_ld, const float* scale, const float* shift, const float* mean,
+                     const float* invstd, const float* gamma, int N, int C, int H, int W, float slope,
+                     const float* g0, int g0_ld, int g0_c0, int g0_route, const float* g1, int g1_ld, int g1_c0,
+                     int g1_route, double* s1, double* s2, void* dy, int dy_ld, int dy_fmt, float dy_scale,
+                     void* stream);
+int ssp_bn_bwd_finalize(double* s1, double* s2, float* dgamma, float* dbeta, int C, int accumulate, void* stream);
+int ssp_bias_grad_nchw(const float* g_nchw, float* dbias, int N, int C, int HW, int accumulate, void* stream);
+
+/* ---- parameters: weight re-pack from the fp32 master [cout][taps][cin]; optim.SGD (train.py:388) ---- */
+int ssp_pack_weights(const float* w, int cout, int taps, int cin, void* fwd_hi, void* fwd_lo, int fwd_ld,
+                     void* dgrad, int dgrad_ld, int dgrad_fmt, void* stream);
+int ssp_sgd_step_flat(float* p, const float* g, float* v, long long n, float lr, float momentum,
+                      float weight_decay, float grad_scale, void* stream);
+
+/* ---- RegionLoss.forward + build_targets + gradient (region_loss.py:9-175); acc = 8 doubles:
+ *      loss_x, loss_y, loss_conf, nGT, nCorrect, nProposals ---- */
+int ssp_region_loss_fwd_bwd(const float* out_nchw, const float* target, float* grad_nchw_or_null, double* acc,
+                            int B, int num_keypoints, int num_classes, int H, int W, float coord_scale,
+                            float noobject_scale, float object_scale, float thresh, int use_conf,
+                            float grad_scale, void* stream);
+/* ---- get_region_boxes (utils.py:216-296): boxes[B][2K+3] per image, box_global[2K+3] = reference semantics ---- */
+int ssp_region_decode_argmax(const float* out_nchw, int B, int num_keypoints, int num_classes, int H, int W,
+                             int only_objectness, float* boxes, float* best_conf, float* box_global_or_null,
+                             void* stream);
+
+/* ---- pnp (utils.py:86-100 -> cv2.solvePnP ITERATIVE + Rodrigues), compute_projection (utils.py:40-45) ---- */
+int ssp_pnp_batched(const float* points3d, int points3d_shared, const float* points2d, const float* K3x3,
+                    int num_points, long long n, int max_iter, double* R_out, double* t_out,
+                    int* iters_out_or_null, void* stream);
+int ssp_project_points(const float* X, int rows, int nv, const double* Rt, const double* K3x3, long long n,
+                       float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

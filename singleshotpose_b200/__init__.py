@@ -1,0 +1,7 @@
+"""singleshotpose_b200 -- B200-native (sm_100a) implementation of the singleshotpose hot path:
+Darknet-19/YOLO-pose conv stack forward/backward, RegionLoss head, decode and batched PnP, behind the
+reference's Python surface (Darknet, RegionLoss, get_region_boxes, pnp)."""
+from .darknet import Darknet          # noqa: F401
+from .region_loss import RegionLoss   # noqa: F401
+from .optim import FlatSGD            # noqa: F401
+from . import utils, cfg, cfgs, synth  # noqa: F401

@@ -1,0 +1,107 @@
+// extern "C" surface of libssp_b200.so (declared in include/ssp_b200.h): argument plumbing only.
+#include "ssp_common.cuh"
+#include "../../include/ssp_b200.h"
+#include <stdio.h>
+#include <string.h>
+
+namespace ssp {
+static thread_local char g_err[512] = "";
+int fail_cuda(cudaError_t e, const char* file, int line) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d", (int)e, cudaGetErrorString(e), file, line);
+  return SSP_ERR_CUDA;
+}
+int fail_msg(int code, const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); return code; }
+
+int conv_gemm_tc(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
+                 float*, int, long long, int, const float*, double*, double*, cudaStream_t);
+int conv_gemm_simt(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
+                   float*, int, long long, int, const float*, double*, double*, cudaStream_t);
+int wgrad_gemm_tc(const void*, long long, int, int, int, const void*, long long, int, int, int, int, int, int, int, float*, int, int, float, cudaStream_t);
+int wgrad_gemm_simt(const void*, long long, int, int, int, const void*, long long, int, int, int, int, int, int, int, float*, int, int, float, cudaStream_t);
+int pack_input_im2col(const float*, void*, void*, int, int, int, cudaStream_t);
+int pack_nchw(const float*, void*, void*, int, int, int, int, int, int, int, float, cudaStream_t);
+int unpack_nchw(const float*, float*, int, int, int, int, int, int, cudaStream_t);
+int unpack16_nchw(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int bn_finalize(double*, double*, double, const float*, const float*, float*, float*, float, float, int, float*, float*, float*, float*, int, cudaStream_t);
+int bn_apply(const float*, int, const float*, const float*, int, int, int, int, float, void*, void*, int, int, int, void*, void*, int, int, int, cudaStream_t);
+int bn_bwd_reduce(const float*, int, const float*, const float*, const float*, const float*, const float*, int, int, int, int, float,
+                  const float*, int, int, int, const float*, int, int, int, double*, double*, cudaStream_t);
+int bn_bwd_apply(const float*, int, const float*, const float*, const float*, const float*, const float*, int, int, int, int, float,
+                 const float*, int, int, int, const float*, int, int, int, double*, double*, void*, int, int, float, cudaStream_t);
+int bn_bwd_finalize(double*, double*, float*, float*, int, int, cudaStream_t);
+int bias_grad_nchw(const float*, float*, int, int, int, int, cudaStream_t);
+int pack_weights(const float*, int, int, int, void*, void*, int, void*, int, int, cudaStream_t);
+int sgd_step_flat(float*, const float*, float*, long long, float, float, float, float, cudaStream_t);
+int region_loss_fwd_bwd(const float*, const float*, float*, double*, int, int, int, int, int, float, float, float, float, int, float, cudaStream_t);
+int region_decode_argmax(const float*, int, int, int, int, int, int, float*, float*, float*, cudaStream_t);
+int pnp_batched(const float*, int, const float*, const float*, int, long long, int, double*, double*, int*, cudaStream_t);
+int project_points(const float*, int, int, const double*, const double*, long long, float*, cudaStream_t);
+}  // namespace ssp
+
+using namespace ssp;
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" {
+int ssp_version(void) { return 100; }
+const char* ssp_last_error(void) { return g_err; }
+long long ssp_flat_alloc_rows(int N, int H, int W) { return flat_alloc_rows(N, H, W); }
+long long ssp_flat_row(int n, int h, int w, int H, int W) { Geom g{1, H, W}; return g.row(n, h, w); }
+
+int ssp_pack_input_im2col(const float* x, void* hi, void* lo, int N, int H, int W, void* s) { return pack_input_im2col(x, hi, lo, N, H, W, ST(s)); }
+int ssp_pack_nchw(const float* x, void* hi, void* lo, int N, int C, int H, int W, int ld, int c0, int fmt, float scale, void* s) {
+  return pack_nchw(x, hi, lo, N, C, H, W, ld, c0, fmt, scale, ST(s));
+}
+int ssp_unpack_nchw(const float* y, float* out, int N, int C, int H, int W, int ld, int c0, void* s) { return unpack_nchw(y, out, N, C, H, W, ld, c0, ST(s)); }
+int ssp_unpack16_nchw(const void* hi, const void* lo, float* out, int N, int C, int H, int W, int ld, int c0, int fmt, void* s) {
+  return unpack16_nchw(hi, lo, out, N, C, H, W, ld, c0, fmt, ST(s));
+}
+int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo, long long a_rows, int a_ld, int cin, const void* b_hi, const void* b_lo,
+                  int b_rows, int b_ld, int a_fmt, int b_fmt, int N, int H, int W, int taps, int cout, float* out, int out_ld,
+                  long long out_rows, int epi, const float* bias, double* ssum, double* ssq, void* s) {
+  if (impl == SSP_IMPL_SIMT)
+    return conv_gemm_simt(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
+  return conv_gemm_tc(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
+}
+int ssp_wgrad_gemm(int impl, const void* dy, long long dy_rows, int dy_ld, int cout, int dy_fmt, const void* x, long long x_rows, int x_ld,
+                   int cin, int x_fmt, int N, int H, int W, int taps, float* dw, int dw_ld, int cin_store, float scale, void* s) {
+  if (impl == SSP_IMPL_SIMT) return wgrad_gemm_simt(dy, dy_rows, dy_ld, cout, dy_fmt, x, x_rows, x_ld, cin, x_fmt, N, H, W, taps, dw, dw_ld, cin_store, scale, ST(s));
+  return wgrad_gemm_tc(dy, dy_rows, dy_ld, cout, dy_fmt, x, x_rows, x_ld, cin, x_fmt, N, H, W, taps, dw, dw_ld, cin_store, scale, ST(s));
+}
+int ssp_bn_finalize(double* ssum, double* ssq, double count, const float* gamma, const float* beta, float* rm, float* rv, float momentum,
+                    float eps, int train, float* mean, float* invstd, float* scale, float* shift, int C, void* s) {
+  return bn_finalize(ssum, ssq, count, gamma, beta, rm, rv, momentum, eps, train, mean, invstd, scale, shift, C, ST(s));
+}
+int ssp_bn_apply(const float* y, int y_ld, const float* scale, const float* shift, int N, int C, int H, int W, float slope,
+                 void* d0_hi, void* d0_lo, int d0_ld, int d0_c0, int d0_route, void* d1_hi, void* d1_lo, int d1_ld, int d1_c0, int d1_route, void* s) {
+  return bn_apply(y, y_ld, scale, shift, N, C, H, W, slope, d0_hi, d0_lo, d0_ld, d0_c0, d0_route, d1_hi, d1_lo, d1_ld, d1_c0, d1_route, ST(s));
+}
+int ssp_bn_bwd_reduce(const float* y, int y_ld, const float* scale, const float* shift, const float* mean, const float* invstd, const float* gamma,
+                      int N, int C, int H, int W, float slope, const float* g0, int g0_ld, int g0_c0, int g0_route,
+                      const float* g1, int g1_ld, int g1_c0, int g1_route, double* s1, double* s2, void* s) {
+  return bn_bwd_reduce(y, y_ld, scale, shift, mean, invstd, gamma, N, C, H, W, slope, g0, g0_ld, g0_c0, g0_route, g1, g1_ld, g1_c0, g1_route, s1, s2, ST(s));
+}
+int ssp_bn_bwd_apply(const float* y, int y_ld, const float* scale, const float* shift, const float* mean, const float* invstd, const float* gamma,
+                     int N, int C, int H, int W, float slope, const float* g0, int g0_ld, int g0_c0, int g0_route,
+                     const float* g1, int g1_ld, int g1_c0, int g1_route, double* s1, double* s2, void* dy, int dy_ld, int dy_fmt, float dy_scale, void* s) {
+  return bn_bwd_apply(y, y_ld, scale, shift, mean, invstd, gamma, N, C, H, W, slope, g0, g0_ld, g0_c0, g0_route, g1, g1_ld, g1_c0, g1_route, s1, s2, dy, dy_ld, dy_fmt, dy_scale, ST(s));
+}
+int ssp_bn_bwd_finalize(double* s1, double* s2, float* dgamma, float* dbeta, int C, int accumulate, void* s) { return bn_bwd_finalize(s1, s2, dgamma, dbeta, C, accumulate, ST(s)); }
+int ssp_bias_grad_nchw(const float* g, float* db, int N, int C, int HW, int accumulate, void* s) { return bias_grad_nchw(g, db, N, C, HW, accumulate, ST(s)); }
+int ssp_pack_weights(const float* w, int cout, int taps, int cin, void* f_hi, void* f_lo, int ld_f, void* d, int ld_d, int d_fmt, void* s) {
+  return pack_weights(w, cout, taps, cin, f_hi, f_lo, ld_f, d, ld_d, d_fmt, ST(s));
+}
+int ssp_sgd_step_flat(float* p, const float* g, float* v, long long n, float lr, float mu, float wd, float gscale, void* s) { return sgd_step_flat(p, g, v, n, lr, mu, wd, gscale, ST(s)); }
+int ssp_region_loss_fwd_bwd(const float* out, const float* target, float* grad, double* acc, int B, int K, int nC, int H, int W, float coord_scale,
+                            float noobject_scale, float object_scale, float thresh, int use_conf, float grad_scale, void* s) {
+  return region_loss_fwd_bwd(out, target, grad, acc, B, K, nC, H, W, coord_scale, noobject_scale, object_scale, thresh, use_conf, grad_scale, ST(s));
+}
+int ssp_region_decode_argmax(const float* out, int B, int K, int nC, int H, int W, int only_objectness, float* boxes, float* best_conf, float* box_global, void* s) {
+  return region_decode_argmax(out, B, K, nC, H, W, only_objectness, boxes, best_conf, box_global, ST(s));
+}
+int ssp_pnp_batched(const float* P3, int shared, const float* uv, const float* K, int np, long long n, int max_iter, double* R, double* t, int* iters, void* s) {
+  return pnp_batched(P3, shared, uv, K, np, n, max_iter, R, t, iters, ST(s));
+}
+int ssp_project_points(const float* X, int rows, int nv, const double* Rt, const double* K, long long n, float* out, void* s) {
+  return project_points(X, rows, nv, Rt, K, n, out, ST(s));
+}
+}

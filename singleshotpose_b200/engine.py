@@ -1,0 +1,372 @@
+"""Execution plan of the yolo-pose conv stack on the sm_100a kernels (libssp_b200.so).
+
+Turns the cfg block list into a per-conv-layer program:
+
+  forward   conv GEMM (tcgen05, split-fp16 3-term) -> fp32 Y (+ per-channel batch statistics in the epilogue)
+            -> bn_finalize -> bn_apply (+LeakyReLU, fused 2x2 max-pool / reorg / concat placement) which
+            writes the NEXT layers' operand planes directly (route / reorg / maxpool blocks never run as
+            kernels of their own; reference darknet.py:82-130 walks them one by one).
+  backward  bn_bwd_reduce / bn_bwd_apply (BN + leaky + pool/reorg/route routing in one pass) -> dY plane
+            -> wgrad GEMM (dW, fp32 atomics into the flat gradient buffer) and dgrad GEMM (dX, fp32).
+
+All parameters live in ONE flat fp32 buffer (conv weights stored [cout][kh][kw][cin]; the nn.Parameter the
+user sees is a permuted view with the reference's OIHW shape), all gradients in a second flat buffer: one
+NCCL all-reduce and one fused SGD kernel per step (train.py:388).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+from .cfg import layer_shapes
+
+
+def _rup(x, m):
+    return (x + m - 1) // m * m
+
+
+class ConvLayer:
+    """Static description of one [convolutional] block (stride 1, 1x1 or 3x3 'same')."""
+
+    def __init__(self, block_ind, cin, cout, size, bn, slope, H, W):
+        self.block_ind, self.cin, self.cout, self.size = block_ind, cin, cout, size
+        self.bn, self.slope, self.H, self.W = bn, slope, H, W
+        self.taps = size * size
+        self.leaves = []      # inputs: (producer layer index or -1 for the image, route kind, channel offset, channels)
+        self.dests = []       # outputs: (consumer layer index, channel offset, route kind)
+        self.first = False
+        # GEMM view of the forward pass
+        self.k_cin = cin      # channels per tap seen by the GEMM (32 for the im2col'ed first layer)
+        self.k_taps = self.taps
+
+
+def build_plan(blocks):
+    """blocks (cfg.parse_cfg) -> list[ConvLayer] in execution order."""
+    shapes = layer_shapes(blocks)
+    exprs = []          # per block: expression tree of its output
+    layers = []
+    cur = ("input", int(blocks[0].get("channels", 3)))
+    for ind, (block, sh) in enumerate(zip(blocks[1:], shapes)):
+        t = block["type"]
+        kind, ic, oc, ih, iw, oh, ow, ex = sh
+        if t == "convolutional":
+            if ex["stride"] != 1 or ex["size"] not in (1, 3) or (ex["size"] == 3 and ex["pad"] != 1):
+                raise NotImplementedError("conv block %d: only stride-1 1x1 / 3x3-same convolutions are on the hot path" % ind)
+            act = block.get("activation", "linear")
+            if act not in ("leaky", "linear"):
+                raise NotImplementedError("activation %r" % act)
+            L = ConvLayer(ind, ic, oc, ex["size"], int(block["batch_normalize"]) == 1, 0.1 if act == "leaky" else 1.0, ih, iw)
+            L.index = len(layers)
+            L.leaves = _flatten(cur)
+            layers.append(L)
+            cur = ("conv", L.index, oc)
+        elif t == "maxpool":
+            if ex["size"] != 2 or ex["stride"] != 2:
+                raise NotImplementedError("maxpool block %d: only 2x2 stride 2" % ind)
+            cur = ("pool", cur)
+        elif t == "reorg":
+            if ex["stride"] != 2:
+                raise NotImplementedError("reorg stride != 2")
+            cur = ("reorg", cur)
+        elif t == "route":
+            ls = ex["layers"]
+            cur = exprs[ls[0]] if len(ls) == 1 else ("cat", [exprs[l] for l in ls])
+        elif t == "region":
+            pass
+        else:
+            raise NotImplementedError("block type %r is not on the hot path" % t)
+        exprs.append(cur)
+    if not layers or layers[-1].bn or layers[-1].slope != 1.0 or cur[0] != "conv":
+        raise NotImplementedError("the network must end in a linear, bias-only convolution (region head)")
+    first = layers[0]
+    if first.leaves != [(-1, _lib.ROUTE_DIRECT, 0, first.cin)] or first.size != 3 or first.cin != 3:
+        raise NotImplementedError("first layer must be a 3x3 convolution on the 3-channel image")
+    first.first = True
+    first.k_cin, first.k_taps = 32, 1           # im2col'ed: K = 27 padded to 32, one "tap"
+    for L in layers[1:]:
+        for (src, kind, c0, c) in L.leaves:
+            if src < 0:
+                raise NotImplementedError("only the first layer may read the image")
+            layers[src].dests.append((L.index, c0, kind))
+    for L in layers[:-1]:
+        if not L.bn:
+            raise NotImplementedError("hidden convolution without batch_normalize")
+        if not 1 <= len(L.dests) <= 2:
+            raise NotImplementedError("conv block %d feeds %d consumers (1 or 2 supported)" % (L.block_ind, len(L.dests)))
+    return layers
+
+
+def _flatten(expr, kind=_lib.ROUTE_DIRECT, c0=0):
+    """expression -> [(producer, route kind, channel offset, channels)]"""
+    tag = expr[0]
+    if tag == "input":
+        return [(-1, kind, c0, expr[1])]
+    if tag == "conv":
+        c = expr[2] * (4 if kind == _lib.ROUTE_REORG else 1)
+        return [(expr[1], kind, c0, c)]
+    if tag in ("pool", "reorg"):
+        if kind != _lib.ROUTE_DIRECT:
+            raise NotImplementedError("chained pool/reorg")
+        return _flatten(expr[1], _lib.ROUTE_POOL if tag == "pool" else _lib.ROUTE_REORG, c0)
+    if tag == "cat":
+        out = []
+        for e in expr[1]:
+            part = _flatten(e, kind, c0)
+            out += part
+            c0 += sum(p[3] for p in part)
+        return out
+    raise NotImplementedError(tag)
+
+
+class Buffers:
+    """Device buffers for one input shape (N, H, W); zero-initialised so that pad rows stay zero."""
+
+    def __init__(self, eng, N, H, W, train):
+        dev = eng.device
+        self.N, self.H, self.W = N, H, W
+        self.generation = 0
+        f16 = torch.float16
+        self.x_hi, self.x_lo, self.y, self.rows = [], [], [], []
+        self.dy, self.dx = [], []
+        for L in eng.layers:
+            # spatial size of this layer for the actual input resolution
+            h, w = eng.spatial(L, H, W)
+            rows = _lib.flat_alloc_rows(N, h, w)
+            cin_total = L.k_cin if L.first else L.cin
+            self.rows.append(rows)
+            self.x_hi.append(torch.zeros(rows, cin_total, dtype=f16, device=dev))
+            self.x_lo.append(torch.zeros(rows, cin_total, dtype=f16, device=dev))
+            self.y.append(torch.zeros(rows, _rup(L.cout, 4), dtype=torch.float32, device=dev))
+            if train:
+                self.dy.append(torch.zeros(rows, _rup(L.cout, 8), dtype=eng.grad_dtype, device=dev))
+                self.dx.append(None if L.first else torch.zeros(rows, cin_total, dtype=torch.float32, device=dev))
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self.layers = build_plan(model.blocks)
+        self.device = None
+        self.flat_params = None
+        self.flat_grads = None
+        self._views = None
+        self._buffers = {}
+        self._weights_version = None
+        impl = os.environ.get("SSP_CONV_IMPL", "tc").lower()
+        self.conv_impl = _lib.IMPL_SIMT if impl == "simt" else _lib.IMPL_TC
+        wimpl = os.environ.get("SSP_WGRAD_IMPL", impl).lower()
+        self.wgrad_impl = _lib.IMPL_SIMT if wimpl == "simt" else _lib.IMPL_TC
+        gfmt = os.environ.get("SSP_GRAD_FMT", "bf16").lower()
+        self.grad_fmt = _lib.FMT_F16 if gfmt in ("f16", "fp16") else _lib.FMT_BF16
+        self.grad_dtype = torch.float16 if self.grad_fmt == _lib.FMT_F16 else torch.bfloat16
+        self.fast = os.environ.get("SSP_PRECISION", "parity").lower() == "fast"   # single-term forward (no hi/lo)
+        self.launches = 0
+        net = model.blocks[0]
+        self.base_hw = (int(net["height"]), int(net["width"]))
+
+    # ------------------------------------------------------------------ geometry
+    def spatial(self, L, H, W):
+        """spatial size of layer L when the network input is H x W (cfg sizes scale with the /2 pools)."""
+        bh, bw = self.base_hw
+        if (H * L.H) % bh or (W * L.W) % bw:
+            raise ValueError("input %dx%d is not compatible with the cfg's pooling pyramid" % (H, W))
+        return H * L.H // bh, W * L.W // bw
+
+    # ------------------------------------------------------------------ parameters
+    def conv_modules(self):
+        out = []
+        for L in self.layers:
+            seq = self.model.models[L.block_ind]
+            out.append((seq[0], seq[1] if L.bn else None))
+        return out
+
+    def materialize(self, device):
+        """Move all parameters into one flat fp32 buffer on `device` (conv weights as [co][kh][kw][ci]) and make the
+        nn.Parameters views of it; idempotent (checked through data_ptr)."""
+        params = list(self.model.parameters())
+        if self.flat_params is not None and self.flat_params.device == device and self._views is not None:
+            if all(p.data_ptr() == v for p, v in zip(params, self._views)):
+                return
+        total = sum(p.numel() for p in params)
+        flat = torch.empty(total, dtype=torch.float32, device=device)
+        grads = torch.zeros(total, dtype=torch.float32, device=device)
+        conv_w = {id(c.weight) for c, _ in self.conv_modules()}
+        off = 0
+        self._slices = {}
+        views = []
+        for p in params:
+            n = p.numel()
+            if id(p) in conv_w:
+                co, ci, kh, kw = p.shape
+                view = flat[off:off + n].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+                gview = grads[off:off + n].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+            else:
+                view = flat[off:off + n].view(p.shape)
+                gview = grads[off:off + n].view(p.shape)
+            view.copy_(p.data.to(device=device, dtype=torch.float32))
+            p.data = view
+            p.grad = None
+            self._slices[id(p)] = (off, n, gview)
+            views.append(view.data_ptr())
+            off += n
+        for _, bn in self.conv_modules():
+            if bn is not None:
+                bn.running_mean.data = bn.running_mean.data.to(device=device, dtype=torch.float32).contiguous()
+                bn.running_var.data = bn.running_var.data.to(device=device, dtype=torch.float32).contiguous()
+        self.flat_params, self.flat_grads, self._views, self.device = flat, grads, views, device
+        self._alloc_layer_state(device)
+        self._buffers = {}
+        self._weights_version = None
+
+    def _alloc_layer_state(self, dev):
+        self.w_hi, self.w_lo, self.w_d, self.stat = [], [], [], []
+        f16 = torch.float16
+        for L in self.layers:
+            kf = _rup(L.k_taps * L.k_cin if not L.first else 32, 8)
+            self.w_hi.append(torch.zeros(L.cout, kf, dtype=f16, device=dev))
+            self.w_lo.append(torch.zeros(L.cout, kf, dtype=f16, device=dev))
+            self.w_d.append(None if L.first else torch.zeros(L.cin, _rup(L.taps * L.cout, 8), dtype=self.grad_dtype, device=dev))
+            st = {}
+            for k in ("ssum", "ssq", "s1", "s2"):
+                st[k] = torch.zeros(L.cout, dtype=torch.float64, device=dev)
+            for k in ("mean", "invstd", "scale", "shift"):
+                st[k] = torch.zeros(L.cout, dtype=torch.float32, device=dev)
+            self.stat.append(st)
+
+    def grad_view(self, p):
+        return self._slices[id(p)][2]
+
+    def _params_version(self):
+        return tuple(p._version for p in self.model.parameters())
+
+    def pack_weights(self, force=False):
+        ver = self._params_version()
+        if not force and ver == self._weights_version:
+            return
+        s = stream_ptr()
+        for L, (conv, _) in zip(self.layers, self.conv_modules()):
+            i = L.index
+            off, n, _g = self._slices[id(conv.weight)]
+            w = self.flat_params[off:off + n]
+            if L.first:    # [32][9][3] -> K = 27 (+5 zeros): a 1-tap GEMM over the im2col'ed input
+                call("ssp_pack_weights", ptr(w), L.cout, 1, 27, ptr(self.w_hi[i]), ptr(self.w_lo[i]), self.w_hi[i].shape[1],
+                     None, 0, 0, s)
+            else:
+                call("ssp_pack_weights", ptr(w), L.cout, L.taps, L.cin, ptr(self.w_hi[i]), ptr(self.w_lo[i]), self.w_hi[i].shape[1],
+                     ptr(self.w_d[i]), self.w_d[i].shape[1], self.grad_fmt, s)
+            self.launches += 1
+        self._weights_version = ver
+
+    def buffers(self, N, H, W, train):
+        key = (N, H, W, bool(train))
+        b = self._buffers.get(key)
+        if b is None:
+            if len(self._buffers) >= 4:
+                self._buffers.clear()
+            b = Buffers(self, N, H, W, train)
+            self._buffers[key] = b
+        return b
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, train_bn, keep_for_backward):
+        """x: (N,3,H,W) fp32 CUDA -> logits (N,Cout,h,w) fp32.  train_bn: batch statistics + running-stat update."""
+        if not x.is_cuda:
+            raise _lib.SspError("singleshotpose_b200 runs on CUDA tensors only (no CPU fallback); got a CPU tensor")
+        x = x.contiguous().float()
+        N, C, H, W = x.shape
+        self.materialize(x.device)
+        self.pack_weights()
+        B = self.buffers(N, H, W, keep_for_backward)
+        B.generation += 1
+        s = stream_ptr()
+        mods = self.conv_modules()
+        call("ssp_pack_input_im2col", ptr(x), ptr(B.x_hi[0]), ptr(B.x_lo[0]), N, H, W, s)
+        self.launches += 1
+        for L in self.layers:
+            i = L.index
+            conv, bn = mods[i]
+            h, w = self.spatial(L, H, W)
+            st = self.stat[i]
+            a_lo = None if self.fast else ptr(B.x_lo[i])
+            b_lo = None if self.fast else ptr(self.w_lo[i])
+            xin = B.x_hi[i]
+            if L.bn:
+                epi = _lib.EPI_STATS if train_bn else _lib.EPI_F32
+                bias = None
+            else:
+                epi, bias = _lib.EPI_BIAS, ptr(conv.bias.data)
+            call("ssp_conv_gemm", self.conv_impl, ptr(xin), a_lo, B.rows[i], xin.shape[1], L.k_cin,
+                 ptr(self.w_hi[i]), b_lo, L.cout, self.w_hi[i].shape[1], _lib.FMT_F16, _lib.FMT_F16,
+                 N, h, w, L.k_taps, L.cout, ptr(B.y[i]), B.y[i].shape[1], B.rows[i], epi, bias,
+                 ptr(st["ssum"]), ptr(st["ssq"]), s)
+            self.launches += 1
+            if not L.bn:
+                continue
+            call("ssp_bn_finalize", ptr(st["ssum"]), ptr(st["ssq"]), float(N * h * w), ptr(bn.weight.data), ptr(bn.bias.data),
+                 ptr(bn.running_mean), ptr(bn.running_var), float(bn.momentum if bn.momentum is not None else 0.1), float(bn.eps),
+                 1 if train_bn else 0, ptr(st["mean"]), ptr(st["invstd"]), ptr(st["scale"]), ptr(st["shift"]), L.cout, s)
+            d = []
+            for (ci, c0, kind) in L.dests:
+                d += [ptr(B.x_hi[ci]), ptr(B.x_lo[ci]), B.x_hi[ci].shape[1], c0, kind]
+            if len(L.dests) == 1:
+                d += [None, None, 0, 0, _lib.ROUTE_NONE]
+            call("ssp_bn_apply", ptr(B.y[i]), B.y[i].shape[1], ptr(st["scale"]), ptr(st["shift"]), N, L.cout, h, w, L.slope, *d, s)
+            self.launches += 2
+        last = self.layers[-1]
+        h, w = self.spatial(last, H, W)
+        out = torch.empty(N, last.cout, h, w, dtype=torch.float32, device=x.device)
+        call("ssp_unpack_nchw", ptr(B.y[-1]), ptr(out), N, last.cout, h, w, B.y[-1].shape[1], 0, s)
+        self.launches += 1
+        return out, B, B.generation
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, B, generation, grad_out):
+        """grad_out: (N,Cout,h,w) fp32 -> fills self.flat_grads (dW for every conv, dgamma/dbeta, dbias)."""
+        if B.generation != generation:
+            raise RuntimeError("activations of this forward pass were overwritten by a later forward of the same shape")
+        N, H, W = B.N, B.H, B.W
+        s = stream_ptr()
+        mods = self.conv_modules()
+        self.flat_grads.zero_()
+        g = grad_out.contiguous().float()
+        for L in reversed(self.layers):
+            i = L.index
+            conv, bn = mods[i]
+            h, w = self.spatial(L, H, W)
+            st = self.stat[i]
+            dy = B.dy[i]
+            if L.bn:
+                srcs = []
+                for (ci, c0, kind) in L.dests:
+                    srcs += [ptr(B.dx[ci]), B.dx[ci].shape[1], c0, kind]
+                if len(L.dests) == 1:
+                    srcs += [None, 0, 0, _lib.ROUTE_NONE]
+                common = [ptr(B.y[i]), B.y[i].shape[1], ptr(st["scale"]), ptr(st["shift"]), ptr(st["mean"]), ptr(st["invstd"]),
+                          ptr(bn.weight.data), N, L.cout, h, w, L.slope, *srcs, ptr(st["s1"]), ptr(st["s2"])]
+                call("ssp_bn_bwd_reduce", *common, s)
+                call("ssp_bn_bwd_apply", *common, ptr(dy), dy.shape[1], self.grad_fmt, 1.0, s)
+                call("ssp_bn_bwd_finalize", ptr(st["s1"]), ptr(st["s2"]), ptr(self.grad_view(bn.weight)), ptr(self.grad_view(bn.bias)),
+                     L.cout, 0, s)
+                self.launches += 3
+            else:
+                call("ssp_pack_nchw", ptr(g), ptr(dy), None, N, L.cout, h, w, dy.shape[1], 0, self.grad_fmt, 1.0, s)
+                call("ssp_bias_grad_nchw", ptr(g), ptr(self.grad_view(conv.bias)), N, L.cout, h * w, 0, s)
+                self.launches += 2
+            off, n, _gv = self._slices[id(conv.weight)]
+            dw = self.flat_grads[off:off + n]
+            xh = B.x_hi[i]
+            if L.first:
+                call("ssp_wgrad_gemm", self.wgrad_impl, ptr(dy), B.rows[i], dy.shape[1], L.cout, self.grad_fmt, ptr(xh), B.rows[i],
+                     xh.shape[1], 32, _lib.FMT_F16, N, h, w, 1, ptr(dw), 27, 27, 1.0, s)
+            else:
+                call("ssp_wgrad_gemm", self.wgrad_impl, ptr(dy), B.rows[i], dy.shape[1], L.cout, self.grad_fmt, ptr(xh), B.rows[i],
+                     xh.shape[1], L.cin, _lib.FMT_F16, N, h, w, L.taps, ptr(dw), L.cin, L.cin, 1.0, s)
+                wd = self.w_d[i]
+                call("ssp_conv_gemm", self.conv_impl, ptr(dy), None, B.rows[i], dy.shape[1], L.cout, ptr(wd), None, L.cin, wd.shape[1],
+                     self.grad_fmt, self.grad_fmt, N, h, w, L.taps, L.cin, ptr(B.dx[i]), B.dx[i].shape[1], B.rows[i], _lib.EPI_F32,
+                     None, None, None, s)
+                self.launches += 1
+            self.launches += 1

@@ -1,0 +1,36 @@
+"""Fused SGD over the engine's flat parameter / gradient buffers: optim.SGD(momentum, dampening=0, weight_decay)
+of train.py:388 as ONE kernel (read p, g, v; write p, v), plus the optional NCCL gradient all-reduce for
+one-process-per-GPU data parallelism (sum over ranks, lr already divided by the global batch)."""
+from __future__ import annotations
+
+import torch
+
+from ._lib import call, ptr, stream_ptr
+
+
+class FlatSGD:
+    def __init__(self, model, lr, momentum=0.0, weight_decay=0.0):
+        self.model = model
+        self.param_groups = [dict(lr=lr, momentum=momentum, weight_decay=weight_decay)]   # adjust_learning_rate() writes lr here
+        self._v = None
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.model.parameters():
+            p.grad = None
+
+    def all_reduce_grads(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.model._engine.flat_grads, op=dist.ReduceOp.SUM)
+
+    def step(self, grad_scale=1.0):
+        eng = self.model._engine
+        if eng.flat_params is None:
+            raise RuntimeError("FlatSGD.step() before the first forward pass")
+        if self._v is None or self._v.data_ptr() == 0 or self._v.numel() != eng.flat_params.numel() or self._v.device != eng.flat_params.device:
+            self._v = torch.zeros_like(eng.flat_params)
+        g = self.param_groups[0]
+        call("ssp_sgd_step_flat", ptr(eng.flat_params), ptr(eng.flat_grads), ptr(self._v), eng.flat_params.numel(),
+             float(g["lr"]), float(g["momentum"]), float(g["weight_decay"]), float(grad_scale), stream_ptr())
+        eng.launches += 1
+        eng._weights_version = None            # the next forward re-packs the fp16 operand copies of the weights

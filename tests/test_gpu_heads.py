@@ -1,0 +1,111 @@
+"""GPU parity of the loss head, decode and PnP kernels against the oracle and the reference-generated goldens."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import region_loss_ref as RL
+from oracle.decode_ref import get_region_boxes_ref
+from oracle.pnp_ref import pnp_ref
+from singleshotpose_b200 import RegionLoss, synth, utils
+
+pytestmark = pytest.mark.gpu
+
+
+def _ang(Ra, Rb):
+    return np.degrees(np.arccos(np.clip((np.trace(Ra @ Rb.T) - 1) / 2, -1, 1)))
+
+
+@pytest.mark.parametrize("epoch", [0, 20])
+def test_region_loss_matches_golden(golden_dir, epoch, capsys):
+    g = np.load(os.path.join(golden_dir, "region_loss.npz"))
+    out = torch.from_numpy(g["output"]).cuda().requires_grad_(True)
+    tgt = torch.from_numpy(g["target"])                       # stays on the CPU like train.py:82-97
+    crit = RegionLoss()
+    loss = crit(out, tgt, epoch)
+    loss.backward()
+    assert float(loss) == pytest.approx(float(g["loss_e%d" % epoch]), rel=1e-4)          # tolerance: 1e-3 (north star)
+    ref = g["grad_e%d" % epoch]
+    assert np.abs(out.grad.cpu().numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
+    st = crit.stats()
+    assert [st["nGT"], st["nCorrect"], st["nProposals"]] == list(g["counters_e%d" % epoch])
+    np.testing.assert_allclose([st["loss_x"], st["loss_y"], st["loss_conf"]], g["parts_e%d" % epoch], rtol=1e-4)
+    assert "nGT 6, recall 1, proposals 954" in capsys.readouterr().out                    # the reference's log line
+
+
+def test_region_loss_matches_oracle_random():
+    for seed in range(3):
+        gen = torch.Generator().manual_seed(100 + seed)
+        B = 5
+        out = torch.randn(B, 20, 13, 13, generator=gen)
+        tgt = synth.targets(B, seed=200 + seed)
+        o = out.clone().requires_grad_(True)
+        l_ref, info = RL.region_loss_ref(o, tgt, 20)
+        l_ref.backward()
+        crit = RegionLoss(); crit.verbose = False
+        od = out.cuda().requires_grad_(True)
+        l = crit(od, tgt.double(), 20)                         # float64 targets as from the train loader
+        l.backward()
+        assert float(l) == pytest.approx(float(l_ref), rel=1e-4)
+        assert (od.grad.cpu() - o.grad).abs().max() <= 1e-4 * o.grad.abs().max()
+
+
+def test_get_region_boxes_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "decode.npz"))
+    box = utils.get_region_boxes(torch.from_numpy(g["output"]).cuda(), 1, 9)
+    got = np.array([float(v) for v in box])
+    np.testing.assert_allclose(got, g["box"], rtol=1e-5, atol=1e-6)
+    assert int(box[20]) == int(g["box"][20])
+
+
+def test_get_region_boxes_per_image_and_oracle():
+    gen = torch.Generator().manual_seed(9)
+    out = torch.randn(4, 20, 13, 13, generator=gen)
+    boxes, best, glob = utils.region_boxes_batched(out.cuda(), 1, 9)
+    for b in range(4):
+        ref = np.array([float(v) for v in get_region_boxes_ref(out[b:b + 1], 1, 9)])
+        np.testing.assert_allclose(boxes[b].cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+    ref = np.array([float(v) for v in get_region_boxes_ref(out, 1, 9)])
+    np.testing.assert_allclose(glob.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["s0", "s1"])
+def test_pnp_matches_cv2_golden(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "pnp.npz"))
+    R, t = utils.pnp_batched(g["P3"], g["uv_" + tag], g["K"])
+    R, t = R.cpu().numpy(), t.cpu().numpy()
+    for i in range(64):
+        assert _ang(R[i], g["R_" + tag][i]) < 1e-2                      # degrees  (north star: 1e-2 deg)
+        assert np.abs(t[i] - g["t_" + tag][i]).max() * 1e3 < 1e-2       # mm       (north star: 1e-2 mm)
+
+
+def test_pnp_reference_signature_and_8_points():
+    pr = synth.pnp_problems(4, sigma=0.5, seed=3, with_center=False)    # 8-point variant
+    for i in range(4):
+        R, t = utils.pnp(pr["P3"], pr["uv"][i], pr["K"])
+        assert R.shape == (3, 3) and t.shape == (3, 1) and R.dtype == np.float64
+        Ro, to = pnp_ref(pr["P3"], pr["uv"][i], pr["K"])
+        assert _ang(R, Ro) < 1e-2 and np.abs(t - to).max() * 1e3 < 1e-2
+
+
+def test_pnp_large_batch_properties():
+    """1e5 problems: exact data => the generating pose is recovered; reprojection error is tiny."""
+    pr = synth.pnp_problems(100000, sigma=0.0, seed=5)
+    R, t, iters = utils.pnp_batched(pr["P3"], pr["uv"], pr["K"], return_iters=True)
+    R, t = R.cpu().numpy(), t.cpu().numpy()
+    tr = np.clip((np.einsum("nij,nij->n", R, pr["R"]) - 1) / 2, -1, 1)
+    ang = np.degrees(np.arccos(tr))
+    assert np.percentile(ang, 99.9) < 1e-2 and np.abs(t - pr["t"]).max() * 1e3 < 0.05    # float32 inputs limit exactness
+    assert int(iters.max()) <= 20
+
+
+def test_project_points_matches_numpy():
+    pr = synth.pnp_problems(3, sigma=0.0, seed=1)
+    X = np.concatenate([pr["P3"].T.astype(np.float64), np.ones((1, 9))])
+    Rt = np.concatenate([pr["R"], pr["t"][:, :, None]], axis=2)
+    K = synth.intrinsics()
+    got = utils.project_points_batched(X.astype(np.float32), Rt, K).cpu().numpy()
+    for i in range(3):
+        ref = utils.compute_projection(X, Rt[i], K)
+        np.testing.assert_allclose(got[i], ref, rtol=1e-6, atol=1e-4)

@@ -1,0 +1,237 @@
+"""GPU parity of the individual kernels, called through the C ABI (ctypes), against plain torch fp32 references
+of the same op computed on the CPU, and tensor-core kernels against their CUDA-core twins."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from singleshotpose_b200 import _lib
+from singleshotpose_b200._lib import call, ptr, stream_ptr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def flat_from_nchw(x, ld=None, c0=0, fmt=None, split=True):
+    """NCHW fp32 (cuda) -> padded-flat planes via the pack kernel."""
+    N, C, H, W = x.shape
+    ld = ld or C
+    rows = _lib.flat_alloc_rows(N, H, W)
+    dt = torch.float16 if fmt in (None, _lib.FMT_F16) else torch.bfloat16
+    hi = torch.zeros(rows, ld, dtype=dt, device=DEV)
+    lo = torch.zeros(rows, ld, dtype=dt, device=DEV) if split else None
+    call("ssp_pack_nchw", ptr(x.contiguous()), ptr(hi), ptr(lo), N, C, H, W, ld, c0, _lib.FMT_F16 if fmt is None else fmt, 1.0, stream_ptr())
+    return hi, lo, rows
+
+
+def nchw_from_flat(y, N, C, H, W, c0=0):
+    out = torch.empty(N, C, H, W, dtype=torch.float32, device=DEV)
+    call("ssp_unpack_nchw", ptr(y), ptr(out), N, C, H, W, y.shape[1], c0, stream_ptr())
+    return out
+
+
+def torch_flat_index(N, H, W):
+    n, h, w = torch.meshgrid(torch.arange(N), torch.arange(H), torch.arange(W), indexing="ij")
+    return (n * (H + 1) * (W + 1) + (h + 1) * (W + 1) + (w + 1)).reshape(-1)
+
+
+def test_pack_layout_matches_definition():
+    N, C, H, W = 2, 8, 5, 7
+    x = torch.randn(N, C, H, W, device=DEV)
+    hi, lo, rows = flat_from_nchw(x)
+    v = (hi.float() + lo.float()).cpu()
+    idx = torch_flat_index(N, H, W)
+    ref = x.permute(0, 2, 3, 1).reshape(-1, C).cpu()
+    assert (v[idx] - ref).abs().max() < 1e-6 * ref.abs().max() + 1e-7           # hi+lo carries ~22 bits
+    mask = torch.ones(rows, dtype=torch.bool); mask[idx] = False
+    assert v[mask].abs().max() == 0                                             # pads untouched (zero)
+    back = nchw_from_flat(v.to(DEV).contiguous(), N, C, H, W)
+    assert torch.equal(back.cpu(), v[idx].reshape(N, H, W, C).permute(0, 3, 1, 2))
+
+
+def _pack_w(w, split=True, fmt=_lib.FMT_F16, dgrad=False):
+    """w: OIHW fp32 cuda -> forward operand planes [co][taps*ci] (+ dgrad plane [ci][taps*co])."""
+    co, ci, kh, kw = w.shape
+    taps = kh * kw
+    master = w.permute(0, 2, 3, 1).contiguous()                # [co][kh][kw][ci]
+    ldf = (taps * ci + 7) // 8 * 8
+    hi = torch.zeros(co, ldf, dtype=torch.float16, device=DEV)
+    lo = torch.zeros(co, ldf, dtype=torch.float16, device=DEV)
+    dt = torch.float16 if fmt == _lib.FMT_F16 else torch.bfloat16
+    ldd = (taps * co + 7) // 8 * 8
+    d = torch.zeros(ci, ldd, dtype=dt, device=DEV) if dgrad else None
+    call("ssp_pack_weights", ptr(master), co, taps, ci, ptr(hi), ptr(lo), ldf, ptr(d), ldd, fmt, stream_ptr())
+    return hi, (lo if split else None), d
+
+
+CONV_CASES = [
+    # N, H, W, cin, cout, k, bias
+    (2, 12, 12, 64, 64, 3, False),
+    (1, 13, 13, 128, 256, 3, False),
+    (3, 5, 7, 64, 32, 3, False),
+    (2, 26, 26, 256, 128, 1, False),
+    (2, 13, 13, 1024, 20, 1, True),
+    (1, 13, 13, 1280, 512, 3, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("impl", [_lib.IMPL_SIMT, _lib.IMPL_TC])
+def test_conv_gemm_matches_torch(case, impl):
+    N, H, W, cin, cout, k, use_bias = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g) if use_bias else None
+    ref = F.conv2d(x.double(), w.double(), None if b is None else b.double(), padding=(k - 1) // 2).float()
+    xh, xl, rows = flat_from_nchw(x.to(DEV))
+    wh, wl, _ = _pack_w(w.to(DEV))
+    ldo = (cout + 3) // 4 * 4
+    y = torch.zeros(rows, ldo, device=DEV)
+    ssum = torch.zeros(cout, dtype=torch.float64, device=DEV); ssq = torch.zeros_like(ssum)
+    epi = _lib.EPI_BIAS if use_bias else _lib.EPI_STATS
+    bias = b.to(DEV) if use_bias else None
+    call("ssp_conv_gemm", impl, ptr(xh), ptr(xl), rows, cin, cin, ptr(wh), ptr(wl), cout, wh.shape[1], 0, 0,
+         N, H, W, k * k, cout, ptr(y), ldo, rows, epi, ptr(bias), ptr(ssum), ptr(ssq), stream_ptr())
+    torch.cuda.synchronize()
+    out = nchw_from_flat(y, N, cout, H, W).cpu()
+    scale = ref.abs().max()
+    assert (out - ref).abs().max() / scale < 2e-5, (out - ref).abs().max() / scale
+    if not use_bias:
+        s_ref = ref.double().sum(dim=(0, 2, 3)); q_ref = (ref.double() ** 2).sum(dim=(0, 2, 3))
+        assert (ssum.cpu() - s_ref).abs().max() < 1e-4 * q_ref.max().sqrt() * (N * H * W) ** 0.5
+        assert ((ssq.cpu() - q_ref).abs() / q_ref).max() < 1e-4
+
+
+def test_conv_gemm_single_term_bf16_dgrad_layout():
+    """dX = conv_transpose(dY, W): the forward kernel with the tap-flipped / transposed weight plane."""
+    N, H, W, cin, cout = 2, 13, 13, 128, 64
+    g = torch.Generator().manual_seed(5)
+    dy = torch.randn(N, cout, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    dyq = dy.bfloat16().float(); wq = w.bfloat16().float()
+    ref = F.conv_transpose2d(dyq.double(), wq.double(), padding=1).float()
+    for impl in (_lib.IMPL_SIMT, _lib.IMPL_TC):
+        dyh, _, rows = flat_from_nchw(dy.to(DEV), fmt=_lib.FMT_BF16, split=False)
+        _, _, wd = _pack_w(w.to(DEV), fmt=_lib.FMT_BF16, dgrad=True)
+        dx = torch.zeros(rows, cin, device=DEV)
+        call("ssp_conv_gemm", impl, ptr(dyh), None, rows, cout, cout, ptr(wd), None, cin, wd.shape[1], 1, 1,
+             N, H, W, 9, cin, ptr(dx), cin, rows, _lib.EPI_F32, None, None, None, stream_ptr())
+        torch.cuda.synchronize()
+        out = nchw_from_flat(dx, N, cin, H, W).cpu()
+        assert (out - ref).abs().max() / ref.abs().max() < 1e-4, impl
+
+
+WGRAD_CASES = [(2, 12, 12, 64, 64, 3), (1, 13, 13, 256, 128, 3), (2, 26, 26, 128, 64, 1), (2, 13, 13, 1024, 20, 1), (3, 5, 7, 64, 256, 3)]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+@pytest.mark.parametrize("impl", [_lib.IMPL_SIMT, _lib.IMPL_TC])
+@pytest.mark.parametrize("dyfmt", [_lib.FMT_BF16, _lib.FMT_F16])
+def test_wgrad_gemm_matches_torch(case, impl, dyfmt):
+    N, H, W, cin, cout, k = case
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(N, cin, H, W, generator=g)
+    dy = torch.randn(N, cout, H, W, generator=g)
+    xq = x.half().float()
+    dyq = (dy.bfloat16() if dyfmt == _lib.FMT_BF16 else dy.half()).float()
+    ref = torch.nn.grad.conv2d_weight(xq.double(), (cout, cin, k, k), dyq.double(), padding=(k - 1) // 2).float()
+    xh, _, rows = flat_from_nchw(x.to(DEV), split=False)
+    ld_dy = (cout + 7) // 8 * 8
+    dyh, _, _ = flat_from_nchw(dy.to(DEV), ld=ld_dy, fmt=dyfmt, split=False)
+    dw = torch.zeros(cout, k * k, cin, device=DEV)
+    call("ssp_wgrad_gemm", impl, ptr(dyh), rows, ld_dy, cout, dyfmt, ptr(xh), rows, cin, cin, _lib.FMT_F16,
+         N, H, W, k * k, ptr(dw), cin, cin, 1.0, stream_ptr())
+    torch.cuda.synchronize()
+    out = dw.view(cout, k, k, cin).permute(0, 3, 1, 2).cpu()
+    assert (out - ref).abs().max() / ref.abs().max() < 1e-4
+
+
+def _bn_ref(y, gamma, beta, route):
+    """torch reference of BN(train)+leaky(+pool/reorg) and its autograd."""
+    z = F.batch_norm(y, None, None, gamma, beta, training=True, eps=1e-4)
+    z = F.leaky_relu(z, 0.1)
+    if route == _lib.ROUTE_POOL:
+        return F.max_pool2d(z, 2, 2)
+    if route == _lib.ROUTE_REORG:
+        B, C, H, W = z.shape
+        t = z.view(B, C, H // 2, 2, W // 2, 2).transpose(3, 4).contiguous()
+        t = t.view(B, C, (H // 2) * (W // 2), 4).transpose(2, 3).contiguous()
+        t = t.view(B, C, 4, H // 2, W // 2).transpose(1, 2).contiguous()
+        return t.view(B, 4 * C, H // 2, W // 2)
+    return z
+
+
+@pytest.mark.parametrize("route", [_lib.ROUTE_DIRECT, _lib.ROUTE_POOL, _lib.ROUTE_REORG])
+@pytest.mark.parametrize("C", [32, 256])
+def test_bn_apply_and_backward(route, C):
+    N, H, W = 3, 8, 6
+    g = torch.Generator().manual_seed(11)
+    y = (torch.randn(N, C, H, W, generator=g) * 1.7 + 0.3).requires_grad_(True)
+    gamma = (torch.rand(C, generator=g) + 0.5).requires_grad_(True)
+    gamma.data[::3] *= -1                                       # negative gammas: pooling must act on activated values
+    beta = torch.randn(C, generator=g).requires_grad_(True)
+    out_ref = _bn_ref(y, gamma, beta, route)
+    gup = torch.randn(out_ref.shape, generator=g)
+    out_ref.backward(gup)
+    # ---- device: statistics come from the conv epilogue in production; here computed by torch in fp64 ----
+    yd = y.detach().to(DEV)
+    rows = _lib.flat_alloc_rows(N, H, W)
+    yf = torch.zeros(rows, C, device=DEV)
+    idx = torch_flat_index(N, H, W).to(DEV)
+    yf[idx] = yd.permute(0, 2, 3, 1).reshape(-1, C)
+    ssum = yd.double().sum(dim=(0, 2, 3)).contiguous(); ssq = (yd.double() ** 2).sum(dim=(0, 2, 3)).contiguous()
+    gm, bt = gamma.detach().to(DEV), beta.detach().to(DEV)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    mean, invstd, scale, shift = (torch.zeros(C, device=DEV) for _ in range(4))
+    call("ssp_bn_finalize", ptr(ssum), ptr(ssq), float(N * H * W), ptr(gm), ptr(bt), ptr(rm), ptr(rv), 0.1, 1e-4, 1,
+         ptr(mean), ptr(invstd), ptr(scale), ptr(shift), C, stream_ptr())
+    bn_t = torch.nn.BatchNorm2d(C, eps=1e-4); bn_t.train(); bn_t(y.detach())
+    assert torch.allclose(rm.cpu(), bn_t.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rv.cpu(), bn_t.running_var, rtol=1e-5, atol=1e-6)
+    assert float(ssum.abs().max()) == 0.0                      # accumulators cleared for the next step
+    oN, oC, oH, oW = out_ref.shape
+    orows = _lib.flat_alloc_rows(oN, oH, oW)
+    ohi = torch.zeros(orows, oC, dtype=torch.float16, device=DEV); olo = torch.zeros_like(ohi)
+    call("ssp_bn_apply", ptr(yf), C, ptr(scale), ptr(shift), N, C, H, W, 0.1, ptr(ohi), ptr(olo), oC, 0, route,
+         None, None, 0, 0, 0, stream_ptr())
+    got = torch.empty(oN, oC, oH, oW, device=DEV)
+    call("ssp_unpack16_nchw", ptr(ohi), ptr(olo), ptr(got), oN, oC, oH, oW, oC, 0, 0, stream_ptr())
+    assert (got.cpu() - out_ref.detach()).abs().max() < 2e-5 * out_ref.detach().abs().max()
+    # ---- backward ----
+    gf = torch.zeros(orows, oC, device=DEV)
+    gf[torch_flat_index(oN, oH, oW).to(DEV)] = gup.to(DEV).permute(0, 2, 3, 1).reshape(-1, oC)
+    s1 = torch.zeros(C, dtype=torch.float64, device=DEV); s2 = torch.zeros_like(s1)
+    common = [ptr(yf), C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(gm), N, C, H, W, 0.1,
+              ptr(gf), oC, 0, route, None, 0, 0, 0, ptr(s1), ptr(s2)]
+    call("ssp_bn_bwd_reduce", *common, stream_ptr())
+    dy = torch.zeros(rows, C, dtype=torch.float16, device=DEV)
+    call("ssp_bn_bwd_apply", *common, ptr(dy), C, _lib.FMT_F16, 1.0, stream_ptr())
+    dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    call("ssp_bn_bwd_finalize", ptr(s1), ptr(s2), ptr(dg), ptr(db), C, 0, stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.allclose(dg.cpu(), gamma.grad, rtol=1e-4, atol=1e-4 * gamma.grad.abs().max())
+    assert torch.allclose(db.cpu(), beta.grad, rtol=1e-4, atol=1e-4 * beta.grad.abs().max())
+    dyn = torch.empty(N, C, H, W, device=DEV)
+    call("ssp_unpack16_nchw", ptr(dy), None, ptr(dyn), N, C, H, W, C, 0, 0, stream_ptr())
+    assert (dyn.cpu() - y.grad).abs().max() < 2e-3 * y.grad.abs().max()        # fp16 storage of dY
+
+
+def test_sgd_flat_matches_torch_sgd():
+    n = 100003
+    g = torch.Generator().manual_seed(3)
+    p0 = torch.randn(n, generator=g); p_t = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.SGD([p_t], lr=0.01, momentum=0.9, dampening=0, weight_decay=0.032)
+    p = p0.clone().to(DEV); v = torch.zeros(n, device=DEV)
+    for _ in range(3):
+        gr = torch.randn(n, generator=g)
+        p_t.grad = gr.clone(); opt.step()
+        call("ssp_sgd_step_flat", ptr(p), ptr(gr.to(DEV)), ptr(v), n, 0.01, 0.9, 0.032, 1.0, stream_ptr())
+    assert torch.allclose(p.cpu(), p_t.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_library_reports_errors():
+    with pytest.raises(_lib.SspError):
+        call("ssp_pnp_batched", None, 1, None, None, 9, 1, 20, None, None, None, stream_ptr())
