@@ -80,8 +80,10 @@ int ssp_bn_bwd_apply(const float* y, int y_ld, const float* scale, const float* 
                      const float* g0, int g0_ld, int g0_c0, int g0_route, const float* g1, int g1_ld, int g1_c0,
                      int g1_route, double* s1, double* s2, void* dy, int dy_ld, int dy_fmt, float dy_scale,
                      void* stream);
-int ssp_bn_bwd_finalize(double* s1, double* s2, float* dgamma, float* dbeta, int C, int accumulate, void* stream);
-int ssp_bias_grad_nchw(const float* g_nchw, float* dbias, int N, int C, int HW, int accumulate, void* stream);
+int ssp_bn_bwd_finalize(double* s1, double* s2, float* dgamma, float* dbeta, int C, int accumulate, float scale,
+                        void* stream);
+int ssp_bias_grad_nchw(const float* g_nchw, float* dbias, int N, int C, int HW, int accumulate, float scale,
+                       void* stream);
 
 /* ---- parameters: weight re-pack from the fp32 master [cout][taps][cin]; optim.SGD (train.py:388) ---- */
 int ssp_pack_weights(const float* w, int cout, int taps, int cin, void* fwd_hi, void* fwd_lo, int fwd_ld,

@@ -28,8 +28,8 @@ int bn_bwd_reduce(const float*, int, const float*, const float*, const float*, c
                   const float*, int, int, int, const float*, int, int, int, double*, double*, cudaStream_t);
 int bn_bwd_apply(const float*, int, const float*, const float*, const float*, const float*, const float*, int, int, int, int, float,
                  const float*, int, int, int, const float*, int, int, int, double*, double*, void*, int, int, float, cudaStream_t);
-int bn_bwd_finalize(double*, double*, float*, float*, int, int, cudaStream_t);
-int bias_grad_nchw(const float*, float*, int, int, int, int, cudaStream_t);
+int bn_bwd_finalize(double*, double*, float*, float*, int, int, float, cudaStream_t);
+int bias_grad_nchw(const float*, float*, int, int, int, int, float, cudaStream_t);
 int pack_weights(const float*, int, int, int, void*, void*, int, void*, int, int, cudaStream_t);
 int sgd_step_flat(float*, const float*, float*, long long, float, float, float, float, cudaStream_t);
 int region_loss_fwd_bwd(const float*, const float*, float*, double*, int, int, int, int, int, float, float, float, float, int, float, cudaStream_t);
@@ -85,8 +85,8 @@ int ssp_bn_bwd_apply(const float* y, int y_ld, const float* scale, const float* 
                      const float* g1, int g1_ld, int g1_c0, int g1_route, double* s1, double* s2, void* dy, int dy_ld, int dy_fmt, float dy_scale, void* s) {
   return bn_bwd_apply(y, y_ld, scale, shift, mean, invstd, gamma, N, C, H, W, slope, g0, g0_ld, g0_c0, g0_route, g1, g1_ld, g1_c0, g1_route, s1, s2, dy, dy_ld, dy_fmt, dy_scale, ST(s));
 }
-int ssp_bn_bwd_finalize(double* s1, double* s2, float* dgamma, float* dbeta, int C, int accumulate, void* s) { return bn_bwd_finalize(s1, s2, dgamma, dbeta, C, accumulate, ST(s)); }
-int ssp_bias_grad_nchw(const float* g, float* db, int N, int C, int HW, int accumulate, void* s) { return bias_grad_nchw(g, db, N, C, HW, accumulate, ST(s)); }
+int ssp_bn_bwd_finalize(double* s1, double* s2, float* dgamma, float* dbeta, int C, int accumulate, float scale, void* s) { return bn_bwd_finalize(s1, s2, dgamma, dbeta, C, accumulate, scale, ST(s)); }
+int ssp_bias_grad_nchw(const float* g, float* db, int N, int C, int HW, int accumulate, float scale, void* s) { return bias_grad_nchw(g, db, N, C, HW, accumulate, scale, ST(s)); }
 int ssp_pack_weights(const float* w, int cout, int taps, int cin, void* f_hi, void* f_lo, int ld_f, void* d, int ld_d, int d_fmt, void* s) {
   return pack_weights(w, cout, taps, cin, f_hi, f_lo, ld_f, d, ld_d, d_fmt, ST(s));
 }

@@ -338,24 +338,25 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
 
 // dgamma = S2, dbeta = S1 (accumulate into the gradient buffers), then clear S1/S2.  Launch AFTER bn_bwd_apply.
 __global__ void bn_bwd_finalize_kernel(double* __restrict__ s1, double* __restrict__ s2, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int C, int accumulate) {
+                                       float* __restrict__ dbeta, int C, int accumulate, float scale) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  if (accumulate) { dgamma[c] += (float)s2[c]; dbeta[c] += (float)s1[c]; }
-  else { dgamma[c] = (float)s2[c]; dbeta[c] = (float)s1[c]; }
+  const float a = (float)(s2[c] * (double)scale), b = (float)(s1[c] * (double)scale);
+  if (accumulate) { dgamma[c] += a; dbeta[c] += b; }
+  else { dgamma[c] = a; dbeta[c] = b; }
   s1[c] = 0.0; s2[c] = 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // column sums of an NCHW fp32 tensor over (n, h, w): bias gradient of the linear head (conv 30)
-__global__ void bias_grad_nchw_kernel(const float* __restrict__ g, float* __restrict__ db, int N, int C, int HW, int accumulate) {
+__global__ void bias_grad_nchw_kernel(const float* __restrict__ g, float* __restrict__ db, int N, int C, int HW, int accumulate, float scale) {
   const int c = blockIdx.x;
   double s = 0.0;
   for (int i = threadIdx.x; i < N * HW; i += blockDim.x) s += (double)g[((long long)(i / HW) * C + c) * HW + (i % HW)];
   __shared__ double sm[256];
   sm[threadIdx.x] = s; __syncthreads();
   for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
-  if (threadIdx.x == 0) { if (accumulate) db[c] += (float)sm[0]; else db[c] = (float)sm[0]; }
+  if (threadIdx.x == 0) { const float v = (float)(sm[0] * (double)scale); if (accumulate) db[c] += v; else db[c] = v; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -505,14 +506,14 @@ int bn_bwd_apply(const float* y, int y_ld, const float* scale, const float* shif
   else bn_bwd_apply_kernel<false><<<nblk(total, 256), 256, 0, s>>>(p);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
-int bn_bwd_finalize(double* s1, double* s2, float* dgamma, float* dbeta, int C, int accumulate, cudaStream_t s) {
+int bn_bwd_finalize(double* s1, double* s2, float* dgamma, float* dbeta, int C, int accumulate, float scale, cudaStream_t s) {
   if (!s1 || !s2 || !dgamma || !dbeta) return fail_msg(SSP_ERR_ARG, "bn_bwd_finalize: null pointer");
-  bn_bwd_finalize_kernel<<<nblk(C, 128), 128, 0, s>>>(s1, s2, dgamma, dbeta, C, accumulate);
+  bn_bwd_finalize_kernel<<<nblk(C, 128), 128, 0, s>>>(s1, s2, dgamma, dbeta, C, accumulate, scale);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
-int bias_grad_nchw(const float* g, float* db, int N, int C, int HW, int accumulate, cudaStream_t s) {
+int bias_grad_nchw(const float* g, float* db, int N, int C, int HW, int accumulate, float scale, cudaStream_t s) {
   if (!g || !db) return fail_msg(SSP_ERR_ARG, "bias_grad_nchw: null pointer");
-  bias_grad_nchw_kernel<<<C, 256, 0, s>>>(g, db, N, C, HW, accumulate);
+  bias_grad_nchw_kernel<<<C, 256, 0, s>>>(g, db, N, C, HW, accumulate, scale);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
 int pack_weights(const float* w, int cout, int taps, int cin, void* f_hi, void* f_lo, int ld_f, void* d, int ld_d, int d_fmt, cudaStream_t s) {

@@ -51,7 +51,9 @@ __device__ __forceinline__ float cvt16_to_f32(uint16_t v, int fmt) {
   return fmt == FMT_F16 ? __half2float(__ushort_as_half(v)) : __bfloat162float(__ushort_as_bfloat16(v));
 }
 __device__ __forceinline__ uint16_t cvt_f32_to_16(float f, int fmt) {
-  return fmt == FMT_F16 ? __half_as_ushort(__float2half_rn(f)) : __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  // fp16 saturates instead of overflowing to inf (loss-scaled gradients)
+  return fmt == FMT_F16 ? __half_as_ushort(__float2half_rn(fminf(fmaxf(f, -65504.f), 65504.f)))
+                        : __bfloat16_as_ushort(__float2bfloat16_rn(f));
 }
 // split an fp32 value into fp16 hi + fp16 lo (hi + lo carries ~22 mantissa bits)
 __device__ __forceinline__ void split_f16(float f, uint16_t& hi, uint16_t& lo) {

@@ -36,9 +36,8 @@ class _MaxPoolMarker(nn.Module):
 
 class _DarknetFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, x, *params):
+    def forward(ctx, model, needs_grad, x, *params):
         eng = model._engine
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         out, bufs, gen = eng.forward(x, train_bn=model.training, keep_for_backward=needs_grad)
         ctx.eng, ctx.bufs, ctx.gen, ctx.nparams = eng, bufs, gen, len(params)
         ctx.params = params
@@ -53,8 +52,8 @@ class _DarknetFn(torch.autograd.Function):
         if prev is not None:
             # p.grad already IS the flat gradient buffer (zero_grad(set_to_none=False) / accumulation): add in place
             eng.flat_grads.add_(prev)
-            return (None, None) + tuple(None for _ in range(ctx.nparams))
-        return (None, None) + tuple(eng.grad_view(p) for p in ctx.params)
+            return (None, None, None) + tuple(None for _ in range(ctx.nparams))
+        return (None, None, None) + tuple(eng.grad_view(p) for p in ctx.params)
 
 
 class Darknet(nn.Module):
@@ -142,7 +141,9 @@ class Darknet(nn.Module):
         """(B,3,H,W) CUDA fp32 -> (B, (2K+1+C)*A, H/32, W/32) raw output of the last conv; the region block is skipped
         exactly as in darknet.py:119-120."""
         self.loss = None
-        return _DarknetFn.apply(self, x, *self.parameters())
+        params = tuple(self.parameters())
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)   # grad mode is off inside Function.forward
+        return _DarknetFn.apply(self, needs_grad, x, *params)
 
     def print_network(self):
         print_cfg(self.blocks)

@@ -98,7 +98,10 @@ def test_conv_gemm_matches_torch(case, impl):
     torch.cuda.synchronize()
     out = nchw_from_flat(y, N, cout, H, W).cpu()
     scale = ref.abs().max()
-    assert (out - ref).abs().max() / scale < 2e-5, (out - ref).abs().max() / scale
+    # the tensor core's fp32 accumulation is ~10x less exact than FFMA and grows with K (measured: 5e-6 @ K=1152,
+    # 3.6e-5 @ K=11520; independent of operand scale, i.e. not the fp16 lo parts) -- tolerance scales with K
+    tol = 2e-5 + 5e-9 * cin * k * k
+    assert (out - ref).abs().max() / scale < tol, (out - ref).abs().max() / scale
     if not use_bias:
         s_ref = ref.double().sum(dim=(0, 2, 3)); q_ref = (ref.double() ** 2).sum(dim=(0, 2, 3))
         assert (ssum.cpu() - s_ref).abs().max() < 1e-4 * q_ref.max().sqrt() * (N * H * W) ** 0.5
@@ -129,20 +132,20 @@ WGRAD_CASES = [(2, 12, 12, 64, 64, 3), (1, 13, 13, 256, 128, 3), (2, 26, 26, 128
 
 @pytest.mark.parametrize("case", WGRAD_CASES)
 @pytest.mark.parametrize("impl", [_lib.IMPL_SIMT, _lib.IMPL_TC])
-@pytest.mark.parametrize("dyfmt", [_lib.FMT_BF16, _lib.FMT_F16])
+@pytest.mark.parametrize("dyfmt", [_lib.FMT_BF16, _lib.FMT_F16])      # both operands share the format (mixing is illegal)
 def test_wgrad_gemm_matches_torch(case, impl, dyfmt):
     N, H, W, cin, cout, k = case
     g = torch.Generator().manual_seed(7)
     x = torch.randn(N, cin, H, W, generator=g)
     dy = torch.randn(N, cout, H, W, generator=g)
-    xq = x.half().float()
+    xq = (x.bfloat16() if dyfmt == _lib.FMT_BF16 else x.half()).float()
     dyq = (dy.bfloat16() if dyfmt == _lib.FMT_BF16 else dy.half()).float()
     ref = torch.nn.grad.conv2d_weight(xq.double(), (cout, cin, k, k), dyq.double(), padding=(k - 1) // 2).float()
-    xh, _, rows = flat_from_nchw(x.to(DEV), split=False)
+    xh, _, rows = flat_from_nchw(x.to(DEV), fmt=dyfmt, split=False)
     ld_dy = (cout + 7) // 8 * 8
     dyh, _, _ = flat_from_nchw(dy.to(DEV), ld=ld_dy, fmt=dyfmt, split=False)
     dw = torch.zeros(cout, k * k, cin, device=DEV)
-    call("ssp_wgrad_gemm", impl, ptr(dyh), rows, ld_dy, cout, dyfmt, ptr(xh), rows, cin, cin, _lib.FMT_F16,
+    call("ssp_wgrad_gemm", impl, ptr(dyh), rows, ld_dy, cout, dyfmt, ptr(xh), rows, cin, cin, dyfmt,
          N, H, W, k * k, ptr(dw), cin, cin, 1.0, stream_ptr())
     torch.cuda.synchronize()
     out = dw.view(cout, k, k, cin).permute(0, 3, 1, 2).cpu()
@@ -210,7 +213,7 @@ def test_bn_apply_and_backward(route, C):
     dy = torch.zeros(rows, C, dtype=torch.float16, device=DEV)
     call("ssp_bn_bwd_apply", *common, ptr(dy), C, _lib.FMT_F16, 1.0, stream_ptr())
     dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
-    call("ssp_bn_bwd_finalize", ptr(s1), ptr(s2), ptr(dg), ptr(db), C, 0, stream_ptr())
+    call("ssp_bn_bwd_finalize", ptr(s1), ptr(s2), ptr(dg), ptr(db), C, 0, 1.0, stream_ptr())
     torch.cuda.synchronize()
     assert torch.allclose(dg.cpu(), gamma.grad, rtol=1e-4, atol=1e-4 * gamma.grad.abs().max())
     assert torch.allclose(db.cpu(), beta.grad, rtol=1e-4, atol=1e-4 * beta.grad.abs().max())
