@@ -10,26 +10,39 @@ namespace ssp {
 
 // ------------------------------------------------------------------------------------------------
 // Layer-0 input: NCHW fp32 image -> im2col'ed rows [row(n,h,w)][32] (k = (kh*3+kw)*3 + c, k >= 27 zero), hi/lo fp16.
-__global__ void pack_input_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
-                                         int N, int H, int W) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)N * H * W * 32;
-  if (idx >= total) return;
-  const int k = (int)(idx & 31);
-  long long pix = idx >> 5;
-  const int w = (int)(pix % W); pix /= W;
-  const int h = (int)(pix % H);
-  const int n = (int)(pix / H);
-  float v = 0.f;
-  if (k < 27) {
-    const int c = k % 3, tap = k / 3;
-    const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + (((long long)n * 3 + c) * H + hh) * W + ww);
+__global__ void __launch_bounds__(256) pack_input_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi,
+                                                                uint16_t* __restrict__ lo, int N, int H, int W) {
+  // one thread per pixel: 27 cached reads (neighbouring threads share them), 2 x 64 B of vector stores
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)N * H * W) return;
+  const int w = (int)(pix % W);
+  const int h = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  uint32_t ph[16], pl[16];
+#pragma unroll
+  for (int k2 = 0; k2 < 16; k2++) {
+    uint16_t a[2], b[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int k = 2 * k2 + e;
+      float v = 0.f;
+      if (k < 27) {
+        const int c = k % 3, tap = k / 3;
+        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + (((long long)n * 3 + c) * H + hh) * W + ww);
+      }
+      split_f16(v, a[e], b[e]);
+    }
+    ph[k2] = a[0] | ((uint32_t)a[1] << 16); pl[k2] = b[0] | ((uint32_t)b[1] << 16);
   }
   Geom g{N, H, W};
-  uint16_t a, b; split_f16(v, a, b);
-  const long long o = g.row(n, h, w) * 32 + k;
-  hi[o] = a; lo[o] = b;
+  const long long o = g.row(n, h, w) * 32;
+  uint4* dh = reinterpret_cast<uint4*>(hi + o); uint4* dl = reinterpret_cast<uint4*>(lo + o);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    dh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+    dl[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+  }
 }
 
 // generic NCHW fp32 -> padded-flat rows (hi/lo fp16, or a single 16-bit plane in `fmt` when lo == nullptr)
@@ -142,45 +155,89 @@ __device__ __forceinline__ void store4(const ActDst& d, long long row, int c, co
   if (d.lo) *reinterpret_cast<uint2*>(d.lo + o) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
 }
 
-// POOLED = true : one thread = one 2x2 window x 4 channels (needed when any destination is DST_POOL)
+// Thread layout shared by the BN kernels: channel group cgi = tid % CG (4 channels each, consecutive threads on
+// consecutive channels => 16-B vectors of one pixel row are contiguous), pixel lane pl = tid / CG.  A block owns a
+// contiguous range of "units" (pixels, or 2x2 windows when a pooled route is involved) and every thread walks it with
+// stride PL, so the per-channel constants are loaded once per thread and several independent loads are in flight.
+struct UnitWalk {
+  int c, pl, PL; long long begin, end; bool active;
+  __device__ UnitWalk(int C, long long nunits, int per_thread) {
+    const int cgs = C >> 2;
+    const int CG = cgs < 256 ? cgs : 256;
+    PL = 256 / CG;
+    const int cblocks = (cgs + CG - 1) / CG;
+    const int cb = blockIdx.x % cblocks;
+    const long long pb = blockIdx.x / cblocks;
+    const int cgi = threadIdx.x % CG;
+    pl = threadIdx.x / CG;
+    c = (cb * CG + cgi) * 4;
+    const long long per = (long long)PL * per_thread;
+    begin = pb * per; end = begin + per; if (end > nunits) end = nunits;
+    active = c < C && pl < PL;
+  }
+};
+static inline unsigned unit_grid(int C, long long nunits, int per_thread) {
+  const int cgs = C / 4, CG = cgs < 256 ? cgs : 256, PL = 256 / CG;
+  const int cblocks = (cgs + CG - 1) / CG;
+  const long long per = (long long)PL * per_thread;
+  return (unsigned)(((nunits + per - 1) / per) * cblocks);
+}
+#define BN_UNITS_PER_THREAD 8
+
+// POOLED = true : unit = one 2x2 window (needed when any destination is DST_POOL)
 template <bool POOLED>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyParams p) {
-  const int cg = p.C >> 2;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int Hs = POOLED ? p.H / 2 : p.H, Ws = POOLED ? p.W / 2 : p.W;
-  const long long total = (long long)p.N * Hs * Ws * cg;
-  if (idx >= total) return;
-  const int c = (int)(idx % cg) * 4;
-  long long pix = idx / cg;
-  const int ws = (int)(pix % Ws); pix /= Ws;
-  const int hs = (int)(pix % Hs);
-  const int n = (int)(pix / Hs);
+  UnitWalk wk(p.C, (long long)p.N * Hs * Ws, BN_UNITS_PER_THREAD);
+  if (!wk.active) return;
+  const int c = wk.c;
   const float4 sc = *reinterpret_cast<const float4*>(p.scale + c);
   const float4 sh = *reinterpret_cast<const float4*>(p.shift + c);
   Geom g{p.N, p.H, p.W};
   Geom gh{p.N, p.H / 2, p.W / 2};
-  float zmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   constexpr int NP = POOLED ? 4 : 1;
+  constexpr int UNR = POOLED ? 2 : 4;           // 8 / 4 independent 16-B loads in flight per thread
+  for (long long u0 = wk.begin + wk.pl; u0 < wk.end; u0 += (long long)UNR * wk.PL) {
+    float4 yv[UNR][NP]; long long rows[UNR][NP]; int nn[UNR], hh[UNR], ww[UNR]; bool ok[UNR];
 #pragma unroll
-  for (int q = 0; q < NP; q++) {
-    const int h = POOLED ? hs * 2 + (q >> 1) : hs, w = POOLED ? ws * 2 + (q & 1) : ws;
-    const long long row = g.row(n, h, w);
-    const float4 yv = *reinterpret_cast<const float4*>(p.y + row * p.y_ld + c);
-    float z[4] = {leaky(fmaf(yv.x, sc.x, sh.x), p.slope), leaky(fmaf(yv.y, sc.y, sh.y), p.slope),
-                  leaky(fmaf(yv.z, sc.z, sh.z), p.slope), leaky(fmaf(yv.w, sc.w, sh.w), p.slope)};
+    for (int t = 0; t < UNR; t++) {
+      const long long u = u0 + (long long)t * wk.PL;
+      ok[t] = u < wk.end;
+      const unsigned uu = (unsigned)(ok[t] ? u : wk.begin);          // 32-bit index math: 64-bit div/mod is ~10x the cost
+      const unsigned tq = uu / (unsigned)Ws;
+      ww[t] = (int)(uu - tq * (unsigned)Ws); nn[t] = (int)(tq / (unsigned)Hs); hh[t] = (int)(tq - (unsigned)nn[t] * (unsigned)Hs);
 #pragma unroll
-    for (int j = 0; j < 4; j++) zmax[j] = fmaxf(zmax[j], z[j]);
-#pragma unroll
-    for (int d = 0; d < 2; d++) {
-      if (p.dst[d].kind == DST_DIRECT) store4(p.dst[d], row, c, z);
-      else if (p.dst[d].kind == DST_REORG)       // marvis ordering, darknet.py:31-34: ch = ((h%2)*2 + w%2)*C + c
-        store4(p.dst[d], gh.row(n, h >> 1, w >> 1), ((h & 1) * 2 + (w & 1)) * p.C + c, z);
+      for (int q = 0; q < NP; q++) {
+        const int h = POOLED ? hh[t] * 2 + (q >> 1) : hh[t], w = POOLED ? ww[t] * 2 + (q & 1) : ww[t];
+        rows[t][q] = g.row(nn[t], h, w);
+        yv[t][q] = *reinterpret_cast<const float4*>(p.y + rows[t][q] * p.y_ld + c);
+      }
     }
-  }
-  if (POOLED) {
 #pragma unroll
-    for (int d = 0; d < 2; d++)
-      if (p.dst[d].kind == DST_POOL) store4(p.dst[d], gh.row(n, hs, ws), c, zmax);
+    for (int t = 0; t < UNR; t++) {
+      if (!ok[t]) continue;
+      float zmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        const int h = POOLED ? hh[t] * 2 + (q >> 1) : hh[t], w = POOLED ? ww[t] * 2 + (q & 1) : ww[t];
+        const float4 v = yv[t][q];
+        float z[4] = {leaky(fmaf(v.x, sc.x, sh.x), p.slope), leaky(fmaf(v.y, sc.y, sh.y), p.slope),
+                      leaky(fmaf(v.z, sc.z, sh.z), p.slope), leaky(fmaf(v.w, sc.w, sh.w), p.slope)};
+#pragma unroll
+        for (int j = 0; j < 4; j++) zmax[j] = fmaxf(zmax[j], z[j]);
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+          if (p.dst[d].kind == DST_DIRECT) store4(p.dst[d], rows[t][q], c, z);
+          else if (p.dst[d].kind == DST_REORG)     // marvis ordering, darknet.py:31-34: ch = ((h%2)*2 + w%2)*C + c
+            store4(p.dst[d], gh.row(nn[t], h >> 1, w >> 1), ((h & 1) * 2 + (w & 1)) * p.C + c, z);
+        }
+      }
+      if (POOLED) {
+#pragma unroll
+        for (int d = 0; d < 2; d++)
+          if (p.dst[d].kind == DST_POOL) store4(p.dst[d], gh.row(nn[t], hh[t], ww[t]), c, zmax);
+      }
+    }
   }
 }
 
@@ -200,53 +257,70 @@ struct BnBwdParams {
   uint16_t* dy; int dy_ld, dy_fmt; float dy_scale;
 };
 
-template <bool POOLED>
-__device__ __forceinline__ void bn_bwd_gather(const BnBwdParams& p, int n, int hs, int ws, int c,
-                                              float (&dz)[POOLED ? 4 : 1][4], float (&xh)[POOLED ? 4 : 1][4],
-                                              long long (&rows)[POOLED ? 4 : 1]) {
-  constexpr int NP = POOLED ? 4 : 1;
-  Geom g{p.N, p.H, p.W};
-  Geom gh{p.N, p.H / 2, p.W / 2};
-  float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0), mu = sh, is = sc;
+struct BwdConsts { float4 sc, sh, mu, is; };
+__device__ __forceinline__ BwdConsts bwd_consts(const BnBwdParams& p, int c) {
+  BwdConsts k;
+  k.sc = make_float4(1, 1, 1, 1); k.sh = make_float4(0, 0, 0, 0); k.mu = k.sh; k.is = k.sc;
   if (p.has_bn) {
-    sc = *reinterpret_cast<const float4*>(p.scale + c); sh = *reinterpret_cast<const float4*>(p.shift + c);
-    mu = *reinterpret_cast<const float4*>(p.mean + c); is = *reinterpret_cast<const float4*>(p.invstd + c);
+    k.sc = *reinterpret_cast<const float4*>(p.scale + c); k.sh = *reinterpret_cast<const float4*>(p.shift + c);
+    k.mu = *reinterpret_cast<const float4*>(p.mean + c); k.is = *reinterpret_cast<const float4*>(p.invstd + c);
   }
-  float z[NP][4];
+  return k;
+}
+
+// one unit (pixel or 2x2 window) of the backward pass: all global loads first, arithmetic afterwards
+template <bool POOLED>
+struct BwdUnit {
+  static constexpr int NP = POOLED ? 4 : 1;
+  float4 y[NP], gd[2][NP], gp[2];
+  long long rows[NP];
+  bool ok;
+  __device__ __forceinline__ void load(const BnBwdParams& p, long long u, long long ubegin, long long uend, int Hs, int Ws, int c) {
+    ok = u < uend;
+    const unsigned uu = (unsigned)(ok ? u : ubegin);                 // 32-bit index math (units < 2^31)
+    const unsigned tq = uu / (unsigned)Ws;
+    const int ws = (int)(uu - tq * (unsigned)Ws), n = (int)(tq / (unsigned)Hs), hs = (int)(tq - (unsigned)n * (unsigned)Hs);
+    Geom g{p.N, p.H, p.W};
+    Geom gh{p.N, p.H / 2, p.W / 2};
 #pragma unroll
-  for (int q = 0; q < NP; q++) {
-    const int h = POOLED ? hs * 2 + (q >> 1) : hs, w = POOLED ? ws * 2 + (q & 1) : ws;
-    rows[q] = g.row(n, h, w);
-    const float4 yv = *reinterpret_cast<const float4*>(p.y + rows[q] * p.y_ld + c);
-    z[q][0] = fmaf(yv.x, sc.x, sh.x); z[q][1] = fmaf(yv.y, sc.y, sh.y);
-    z[q][2] = fmaf(yv.z, sc.z, sh.z); z[q][3] = fmaf(yv.w, sc.w, sh.w);
-    xh[q][0] = (yv.x - mu.x) * is.x; xh[q][1] = (yv.y - mu.y) * is.y;
-    xh[q][2] = (yv.z - mu.z) * is.z; xh[q][3] = (yv.w - mu.w) * is.w;
+    for (int q = 0; q < NP; q++) {
+      const int h = POOLED ? hs * 2 + (q >> 1) : hs, w = POOLED ? ws * 2 + (q & 1) : ws;
+      rows[q] = g.row(n, h, w);
+      y[q] = *reinterpret_cast<const float4*>(p.y + rows[q] * p.y_ld + c);
 #pragma unroll
-    for (int j = 0; j < 4; j++) dz[q][j] = 0.f;
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-      const GradSrc& gs = p.src[s];
-      if (gs.kind == SRC_DIRECT) {
-        const float4 gv = *reinterpret_cast<const float4*>(gs.g + rows[q] * gs.ld + gs.c0 + c);
-        dz[q][0] += gv.x; dz[q][1] += gv.y; dz[q][2] += gv.z; dz[q][3] += gv.w;
-      } else if (gs.kind == SRC_REORG) {
-        const float4 gv = *reinterpret_cast<const float4*>(gs.g + gh.row(n, h >> 1, w >> 1) * gs.ld + gs.c0 +
-                                                            ((h & 1) * 2 + (w & 1)) * p.C + c);
-        dz[q][0] += gv.x; dz[q][1] += gv.y; dz[q][2] += gv.z; dz[q][3] += gv.w;
+      for (int s = 0; s < 2; s++) {
+        const GradSrc& gs = p.src[s];
+        gd[s][q] = make_float4(0, 0, 0, 0);
+        if (gs.kind == SRC_DIRECT) gd[s][q] = *reinterpret_cast<const float4*>(gs.g + rows[q] * gs.ld + gs.c0 + c);
+        else if (gs.kind == SRC_REORG)
+          gd[s][q] = *reinterpret_cast<const float4*>(gs.g + gh.row(n, h >> 1, w >> 1) * gs.ld + gs.c0 + ((h & 1) * 2 + (w & 1)) * p.C + c);
       }
     }
-  }
-  if (POOLED) {
 #pragma unroll
     for (int s = 0; s < 2; s++) {
-      const GradSrc& gs = p.src[s];
-      if (gs.kind != SRC_POOL) continue;
-      const float4 gv4 = *reinterpret_cast<const float4*>(gs.g + gh.row(n, hs, ws) * gs.ld + gs.c0 + c);
-      const float gv[4] = {gv4.x, gv4.y, gv4.z, gv4.w};
+      gp[s] = make_float4(0, 0, 0, 0);
+      if (POOLED && p.src[s].kind == SRC_POOL)
+        gp[s] = *reinterpret_cast<const float4*>(p.src[s].g + gh.row(n, hs, ws) * p.src[s].ld + p.src[s].c0 + c);
+    }
+  }
+  // dz = (routed upstream gradient) * leaky'(z);  xh = normalised conv output
+  __device__ __forceinline__ void compute(const BnBwdParams& p, const BwdConsts& k, float (&dz)[NP][4], float (&xh)[NP][4]) const {
+    float z[NP][4];
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+      const float4 yv = y[q];
+      z[q][0] = fmaf(yv.x, k.sc.x, k.sh.x); z[q][1] = fmaf(yv.y, k.sc.y, k.sh.y);
+      z[q][2] = fmaf(yv.z, k.sc.z, k.sh.z); z[q][3] = fmaf(yv.w, k.sc.w, k.sh.w);
+      xh[q][0] = (yv.x - k.mu.x) * k.is.x; xh[q][1] = (yv.y - k.mu.y) * k.is.y;
+      xh[q][2] = (yv.z - k.mu.z) * k.is.z; xh[q][3] = (yv.w - k.mu.w) * k.is.w;
+      dz[q][0] = gd[0][q].x + gd[1][q].x; dz[q][1] = gd[0][q].y + gd[1][q].y;
+      dz[q][2] = gd[0][q].z + gd[1][q].z; dz[q][3] = gd[0][q].w + gd[1][q].w;
+    }
+    if (POOLED) {
+      const float gv[4] = {gp[0].x + gp[1].x, gp[0].y + gp[1].y, gp[0].z + gp[1].z, gp[0].w + gp[1].w};
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        // argmax of the ACTIVATED values; first maximum in (h, w) scan order wins (max_pool2d semantics)
+        // arg-max of the ACTIVATED values; the first maximum in (h, w) scan order wins (max_pool2d semantics)
         int best = 0; float bv = leaky(z[0][j], p.slope);
 #pragma unroll
         for (int q = 1; q < NP; q++) { const float a = leaky(z[q][j], p.slope); if (a > bv) { bv = a; best = q; } }
@@ -254,43 +328,45 @@ __device__ __forceinline__ void bn_bwd_gather(const BnBwdParams& p, int n, int h
         for (int q = 0; q < NP; q++) if (q == best) dz[q][j] += gv[j];
       }
     }
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) dz[q][j] *= (z[q][j] > 0.f ? 1.f : p.slope);
   }
-#pragma unroll
-  for (int q = 0; q < NP; q++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) dz[q][j] *= (z[q][j] > 0.f ? 1.f : p.slope);
-}
+};
+
+#define BWD_REDUCE_UNITS_PER_THREAD 32
 
 template <bool POOLED>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
-  // thread layout: channel group = tid % CG (4 channels each), pixel lane = tid / CG
   extern __shared__ float red[];           // [2][PL][CG*4]
-  const int cgs = p.C >> 2;
-  const int CG = cgs < 256 ? cgs : 256;
-  const int PL = 256 / CG;
-  const int cgi = threadIdx.x % CG, pl = threadIdx.x / CG;
   const int Hs = POOLED ? p.H / 2 : p.H, Ws = POOLED ? p.W / 2 : p.W;
-  const long long npix = (long long)p.N * Hs * Ws;
-  const int cblocks = (cgs + CG - 1) / CG;
-  const int cb = blockIdx.x % cblocks;
-  const int pb = blockIdx.x / cblocks, npb = gridDim.x / cblocks;
-  const int c = (cb * CG + cgi) * 4;
+  UnitWalk wk(p.C, (long long)p.N * Hs * Ws, BWD_REDUCE_UNITS_PER_THREAD);
+  constexpr int NP = POOLED ? 4 : 1;
+  constexpr int UNR = POOLED ? 1 : 4;
+  const int c = wk.c;
   float a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
-  if (c < p.C && pl < PL) {
-    const long long per = (npix + npb - 1) / npb;
-    long long e = (long long)(pb + 1) * per; if (e > npix) e = npix;
-    for (long long pix = (long long)pb * per + pl; pix < e; pix += PL) {
-      const int ws = (int)(pix % Ws); const long long t = pix / Ws;
-      const int hs = (int)(t % Hs); const int n = (int)(t / Hs);
-      float dz[POOLED ? 4 : 1][4], xh[POOLED ? 4 : 1][4]; long long rows[POOLED ? 4 : 1];
-      bn_bwd_gather<POOLED>(p, n, hs, ws, c, dz, xh, rows);
+  if (wk.active) {
+    const BwdConsts k = bwd_consts(p, c);
+    for (long long u0 = wk.begin + wk.pl; u0 < wk.end; u0 += (long long)UNR * wk.PL) {
+      BwdUnit<POOLED> un[UNR];
 #pragma unroll
-      for (int q = 0; q < (POOLED ? 4 : 1); q++)
+      for (int t = 0; t < UNR; t++) un[t].load(p, u0 + (long long)t * wk.PL, wk.begin, wk.end, Hs, Ws, c);
 #pragma unroll
-        for (int j = 0; j < 4; j++) { a1[j] += dz[q][j]; a2[j] += dz[q][j] * xh[q][j]; }
+      for (int t = 0; t < UNR; t++) {
+        if (!un[t].ok) continue;
+        float dz[NP][4], xh[NP][4];
+        un[t].compute(p, k, dz, xh);
+#pragma unroll
+        for (int q = 0; q < NP; q++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) { a1[j] += dz[q][j]; a2[j] = fmaf(dz[q][j], xh[q][j], a2[j]); }
+      }
     }
   }
-  const int CW = CG * 4;
+  const int cgs = p.C >> 2, CG = cgs < 256 ? cgs : 256, PL = 256 / CG, CW = CG * 4;
+  const int cgi = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int cblocks = (cgs + CG - 1) / CG, cb = blockIdx.x % cblocks;
   if (pl < PL) {
 #pragma unroll
     for (int j = 0; j < 4; j++) { red[(0 * PL + pl) * CW + cgi * 4 + j] = a1[j]; red[(1 * PL + pl) * CW + cgi * 4 + j] = a2[j]; }
@@ -298,41 +374,50 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * CW; i += 256) {
     const int which = i / CW, cc = i % CW;
-    double s = 0.0;
-    for (int r = 0; r < PL; r++) s += (double)red[(which * PL + r) * CW + cc];
+    double sacc = 0.0;
+    for (int r = 0; r < PL; r++) sacc += (double)red[(which * PL + r) * CW + cc];
     const int ch = cb * CW + cc;
-    if (ch < p.C) atomicAdd((which ? p.s2 : p.s1) + ch, s);
+    if (ch < p.C) atomicAdd((which ? p.s2 : p.s1) + ch, sacc);
   }
 }
 
 template <bool POOLED>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
-  const int cg = p.C >> 2;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int Hs = POOLED ? p.H / 2 : p.H, Ws = POOLED ? p.W / 2 : p.W;
-  const long long total = (long long)p.N * Hs * Ws * cg;
-  if (idx >= total) return;
-  const int c = (int)(idx % cg) * 4;
-  long long pix = idx / cg;
-  const int ws = (int)(pix % Ws); pix /= Ws;
-  const int hs = (int)(pix % Hs);
-  const int n = (int)(pix / Hs);
-  float dz[POOLED ? 4 : 1][4], xh[POOLED ? 4 : 1][4]; long long rows[POOLED ? 4 : 1];
-  bn_bwd_gather<POOLED>(p, n, hs, ws, c, dz, xh, rows);
-  float k1[4] = {0, 0, 0, 0}, k2[4] = {0, 0, 0, 0}, gs[4] = {1, 1, 1, 1};
+  UnitWalk wk(p.C, (long long)p.N * Hs * Ws, BN_UNITS_PER_THREAD);
+  if (!wk.active) return;
+  constexpr int NP = POOLED ? 4 : 1;
+  constexpr int UNR = POOLED ? 1 : 4;
+  const int c = wk.c;
+  const BwdConsts k = bwd_consts(p, c);
+  float k1[4] = {0, 0, 0, 0}, k2[4] = {0, 0, 0, 0}, gsc[4] = {1, 1, 1, 1};
   if (p.has_bn) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       k1[j] = (float)(p.s1[c + j] / p.count); k2[j] = (float)(p.s2[c + j] / p.count);
-      gs[j] = p.gamma[c + j] * p.invstd[c + j];
+      gsc[j] = p.gamma[c + j] * p.invstd[c + j] * p.dy_scale;
     }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) gsc[j] = p.dy_scale;
   }
+  for (long long u0 = wk.begin + wk.pl; u0 < wk.end; u0 += (long long)UNR * wk.PL) {
+    BwdUnit<POOLED> un[UNR];
 #pragma unroll
-  for (int q = 0; q < (POOLED ? 4 : 1); q++) {
-    uint16_t o[4];
+    for (int t = 0; t < UNR; t++) un[t].load(p, u0 + (long long)t * wk.PL, wk.begin, wk.end, Hs, Ws, c);
 #pragma unroll
-    for (int j = 0; j < 4; j++) o[j] = cvt_f32_to_16(gs[j] * (dz[q][j] - k1[j] - xh[q][j] * k2[j]) * p.dy_scale, p.dy_fmt);
-    *reinterpret_cast<uint2*>(p.dy + rows[q] * p.dy_ld + c) = make_uint2(o[0] | ((uint32_t)o[1] << 16), o[2] | ((uint32_t)o[3] << 16));
+    for (int t = 0; t < UNR; t++) {
+      if (!un[t].ok) continue;
+      float dz[NP][4], xh[NP][4];
+      un[t].compute(p, k, dz, xh);
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        uint16_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[j] = cvt_f32_to_16(gsc[j] * (dz[q][j] - k1[j] - xh[q][j] * k2[j]), p.dy_fmt);
+        *reinterpret_cast<uint2*>(p.dy + un[t].rows[q] * p.dy_ld + c) = make_uint2(o[0] | ((uint32_t)o[1] << 16), o[2] | ((uint32_t)o[3] << 16));
+      }
+    }
   }
 }
 
@@ -409,7 +494,7 @@ static inline unsigned nblk(long long total, int bs) { return (unsigned)((total 
 
 int pack_input_im2col(const float* x, void* hi, void* lo, int N, int H, int W, cudaStream_t s) {
   if (!x || !hi || !lo) return fail_msg(SSP_ERR_ARG, "pack_input_im2col: null pointer");
-  const long long total = (long long)N * H * W * 32;
+  const long long total = (long long)N * H * W;
   pack_input_im2col_kernel<<<nblk(total, 256), 256, 0, s>>>(x, (uint16_t*)hi, (uint16_t*)lo, N, H, W);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
@@ -449,13 +534,8 @@ int bn_apply(const float* y, int y_ld, const float* scale, const float* shift, i
   const bool pooled = p.dst[0].kind == DST_POOL || p.dst[1].kind == DST_POOL;
   const bool halves = pooled || p.dst[0].kind == DST_REORG || p.dst[1].kind == DST_REORG;
   if (halves && ((H | W) & 1)) return fail_msg(SSP_ERR_ARG, "bn_apply: pool/reorg need even H and W");
-  if (pooled) {
-    const long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
-    bn_apply_kernel<true><<<nblk(total, 256), 256, 0, s>>>(p);
-  } else {
-    const long long total = (long long)N * H * W * (C / 4);
-    bn_apply_kernel<false><<<nblk(total, 256), 256, 0, s>>>(p);
-  }
+  if (pooled) bn_apply_kernel<true><<<unit_grid(C, (long long)N * (H / 2) * (W / 2), BN_UNITS_PER_THREAD), 256, 0, s>>>(p);
+  else bn_apply_kernel<false><<<unit_grid(C, (long long)N * H * W, BN_UNITS_PER_THREAD), 256, 0, s>>>(p);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
 
@@ -482,13 +562,11 @@ int bn_bwd_reduce(const float* y, int y_ld, const float* scale, const float* shi
     return fail_msg(SSP_ERR_ARG, "bn_bwd_reduce: bad argument");
   const bool pooled = p.src[0].kind == SRC_POOL || p.src[1].kind == SRC_POOL;
   const int cgs = C / 4, CG = cgs < 256 ? cgs : 256, PL = 256 / CG;
-  const int cblocks = (cgs + CG - 1) / CG;
-  const long long npix = (long long)N * (pooled ? H / 2 : H) * (pooled ? W / 2 : W);
-  long long npb = (npix + (long long)PL * 16 - 1) / ((long long)PL * 16);
-  const long long cap = 148 * 8 / cblocks; if (npb > cap) npb = cap; if (npb < 1) npb = 1;
+  const long long nunits = (long long)N * (pooled ? H / 2 : H) * (pooled ? W / 2 : W);
   const size_t sm = (size_t)2 * PL * CG * 4 * sizeof(float);
-  if (pooled) bn_bwd_reduce_kernel<true><<<(unsigned)(npb * cblocks), 256, sm, s>>>(p);
-  else bn_bwd_reduce_kernel<false><<<(unsigned)(npb * cblocks), 256, sm, s>>>(p);
+  const unsigned grid = unit_grid(C, nunits, BWD_REDUCE_UNITS_PER_THREAD);
+  if (pooled) bn_bwd_reduce_kernel<true><<<grid, 256, sm, s>>>(p);
+  else bn_bwd_reduce_kernel<false><<<grid, 256, sm, s>>>(p);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
 int bn_bwd_apply(const float* y, int y_ld, const float* scale, const float* shift, const float* mean, const float* invstd,
@@ -501,9 +579,10 @@ int bn_bwd_apply(const float* y, int y_ld, const float* scale, const float* shif
   if (p.has_bn && (!s1 || !s2)) return fail_msg(SSP_ERR_ARG, "bn_bwd_apply: statistics buffers missing");
   p.dy = (uint16_t*)dy; p.dy_ld = dy_ld; p.dy_fmt = dy_fmt; p.dy_scale = dy_scale;
   const bool pooled = p.src[0].kind == SRC_POOL || p.src[1].kind == SRC_POOL;
-  const long long total = (long long)N * (pooled ? H / 2 : H) * (pooled ? W / 2 : W) * (C / 4);
-  if (pooled) bn_bwd_apply_kernel<true><<<nblk(total, 256), 256, 0, s>>>(p);
-  else bn_bwd_apply_kernel<false><<<nblk(total, 256), 256, 0, s>>>(p);
+  const long long nunits = (long long)N * (pooled ? H / 2 : H) * (pooled ? W / 2 : W);
+  const unsigned grid = unit_grid(C, nunits, BN_UNITS_PER_THREAD);
+  if (pooled) bn_bwd_apply_kernel<true><<<grid, 256, 0, s>>>(p);
+  else bn_bwd_apply_kernel<false><<<grid, 256, 0, s>>>(p);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
 int bn_bwd_finalize(double* s1, double* s2, float* dgamma, float* dbeta, int C, int accumulate, float scale, cudaStream_t s) {

@@ -4,8 +4,10 @@
 // for the tensor core (channels contiguous, K = rows): the TMA boxes [64 rows][64 channels] land in
 // shared memory exactly in the canonical MN-major SWIZZLE_128B layout, no transposed copies needed.
 // dY has zero pad rows, X has zero pad rows, so the shifted product never picks up wrap-around terms.
-// Work item = (co tile of 128, ci tile of BN, tap, K split); partial sums are reduced with fp32 RED
-// atomics into dW, which the caller zeroes once per step.  Output layout [co][tap][ci] is the layout the
+// Work item = (co tile of 128, ci tile of BN, GROUP of taps, K split): the dY tile is loaded once per k-block and
+// multiplied against the X tiles of all taps of the group, one TMEM accumulator (BN columns) per tap (up to
+// 512/BN taps) -- the kernel is L2->SMEM bandwidth bound, sharing dY across taps is what matters.  Partial sums
+// are reduced with fp32 RED atomics into dW, which the caller zeroes once per step.  Output layout [co][tap][ci] is the layout the
 // master weights are kept in (engine.py), i.e. the gradient of nn.Conv2d.weight seen through a permuted view.
 // Replaces the conv weight-gradient autograd computes for reference train.py:103.
 #include "ssp_common.cuh"
@@ -18,6 +20,7 @@ struct WgradTcParams {
   CUtensorMap tmX;      // [rows][cin]    box {64, 64}
   long long m_rows;
   int co_tiles, ci_tiles, taps, splits;
+  int groups, taps_per_group, nbuf;   // tap groups per (co, ci) tile; accumulator buffers in TMEM (2 if they fit twice)
   int kblocks_total;    // ceil(m_rows / 64)
   int shifts[9];
   int cout, cin, bn;
@@ -42,8 +45,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
   uint32_t* tmem_ptr = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int items = p.co_tiles * p.ci_tiles * p.taps * p.splits;
-  const int nb = p.bn / 64;                         // B boxes per stage
+  const int items = p.co_tiles * p.ci_tiles * p.groups * p.splits;
+  const int nb = p.bn <= 64 ? 1 : p.bn / 64;        // X boxes per tap and stage
   const int kb_per_split = (p.kblocks_total + p.splits - 1) / p.splits;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmDy); tma_prefetch_desc(&p.tmX); }
@@ -59,10 +62,12 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_ptr;
 
   // item -> (split, tap, ci tile, co tile); co fastest so that concurrently running CTAs share X tiles in L2
-  auto decode = [&](int it, int& co_t, int& ci_t, int& tap, int& kb0, int& kb1) {
+  auto decode = [&](int it, int& co_t, int& ci_t, int& tap0, int& ntap, int& kb0, int& kb1) {
     co_t = it % p.co_tiles; it /= p.co_tiles;
     ci_t = it % p.ci_tiles; it /= p.ci_tiles;
-    tap = it % p.taps; it /= p.taps;
+    const int grp = it % p.groups; it /= p.groups;
+    tap0 = grp * p.taps_per_group;
+    ntap = p.taps - tap0 < p.taps_per_group ? p.taps - tap0 : p.taps_per_group;
     kb0 = it * kb_per_split;
     kb1 = kb0 + kb_per_split; if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
   };
@@ -70,9 +75,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)(2 + nb) * kBox;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        int co_t, ci_t, tap, kb0, kb1; decode(it, co_t, ci_t, tap, kb0, kb1);
+        int co_t, ci_t, tap0, ntap, kb0, kb1; decode(it, co_t, ci_t, tap0, ntap, kb0, kb1);
+        const uint32_t tx = (uint32_t)(2 + ntap * nb) * kBox;
         for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = smem + (size_t)stage * p.stage_bytes;
@@ -80,8 +85,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
           const int row = kb * 64;
           tma_load_2d(s, &p.tmDy, &full_bar[stage], co_t * 128, row);
           tma_load_2d(s + kBox, &p.tmDy, &full_bar[stage], co_t * 128 + 64, row);
-          for (int j = 0; j < nb; j++)
-            tma_load_2d(s + (2 + j) * kBox, &p.tmX, &full_bar[stage], ci_t * p.bn + j * 64, row + p.shifts[tap]);
+          for (int t = 0; t < ntap; t++)
+            for (int j = 0; j < nb; j++)
+              tma_load_2d(s + (2 + t * nb + j) * kBox, &p.tmX, &full_bar[stage], ci_t * p.bn + j * 64, row + p.shifts[tap0 + t]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -90,22 +96,25 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0; int n = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x, n++) {
-        int co_t, ci_t, tap, kb0, kb1; decode(it, co_t, ci_t, tap, kb0, kb1);
-        const int buf = n & 1;
-        mbar_wait(&tempty_bar[buf], ((n >> 1) & 1) ^ 1);
+        int co_t, ci_t, tap0, ntap, kb0, kb1; decode(it, co_t, ci_t, tap0, ntap, kb0, kb1);
+        const int buf = n % p.nbuf, use = n / p.nbuf;
+        mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.bn);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.taps_per_group * p.bn);
         uint32_t acc = 0;
         for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t s = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          for (int t = 0; t < ntap; t++) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) {   // 16 K rows per MMA = 2 swizzle groups of 8 rows = 2048 B
-            const uint64_t da = umma_desc_sw128(s + k * 2048, kBox, 1024);
-            const uint64_t db = umma_desc_sw128(s + 2 * kBox + k * 2048, kBox, 1024);
-            umma_f16(d_tmem, da, db, p.idesc, acc); acc = 1;
+            for (int k = 0; k < 4; k++) {   // 16 K rows per MMA = 2 swizzle groups of 8 rows = 2048 B
+              const uint64_t da = umma_desc_sw128(s + k * 2048, kBox, 1024);
+              const uint64_t db = umma_desc_sw128(s + (2 + t * nb) * kBox + k * 2048, kBox, 1024);
+              umma_f16(d_tmem + (uint32_t)(t * p.bn), da, db, p.idesc, (k == 0) ? acc : 1u);
+            }
           }
+          acc = 1;
           umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -116,22 +125,24 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
     const int q = warp - 4;
     int n = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x, n++) {
-      int co_t, ci_t, tap, kb0, kb1; decode(it, co_t, ci_t, tap, kb0, kb1);
-      const int buf = n & 1;
-      mbar_wait(&tfull_bar[buf], (n >> 1) & 1);
+      int co_t, ci_t, tap0, ntap, kb0, kb1; decode(it, co_t, ci_t, tap0, ntap, kb0, kb1);
+      const int buf = n % p.nbuf, use = n / p.nbuf;
+      mbar_wait(&tfull_bar[buf], use & 1);
       tc_fence_after();
       const int co = co_t * 128 + q * 32 + lane;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.bn);
-      float* drow = p.dw + ((long long)co * p.taps + tap) * p.dw_ld;
-      for (int ch = 0; ch < p.bn / 32; ch++) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + ch * 32, r);
-        tmem_ld_wait();
-        const int c0 = ci_t * p.bn + ch * 32;
-        if (co < p.cout && kb1 > kb0) {
+      for (int t = 0; t < ntap; t++) {
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.taps_per_group + t) * p.bn);
+        float* drow = p.dw + ((long long)co * p.taps + tap0 + t) * p.dw_ld;
+        for (int ch = 0; ch < p.bn / 32; ch++) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + ch * 32, r);
+          tmem_ld_wait();
+          const int c0 = ci_t * p.bn + ch * 32;
+          if (co < p.cout && kb1 > kb0) {
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (c0 + j < p.cin_store) atomicAdd(drow + c0 + j, __uint_as_float(r[j]) * p.scale);
+            for (int j = 0; j < 32; j++)
+              if (c0 + j < p.cin_store) atomicAdd(drow + c0 + j, __uint_as_float(r[j]) * p.scale);
+          }
         }
       }
       tc_fence_before();
@@ -160,7 +171,15 @@ int wgrad_gemm_tc(const void* dy, long long dy_rows, int dy_ld, int cout, int dy
   int bn = ((cin + 63) / 64) * 64;
   if (bn > 256) bn = 256;
   if (bn > 128 && bn < 256) bn = 256;
+  if (cin <= 32) bn = 32;             // N = 32 MMAs on the first half of the 64-channel box (rest is TMA zero fill)
   p.bn = bn;
+  const int nb = bn <= 64 ? 1 : bn / 64;
+  // sharing dY across taps pays for narrow tiles (L2-bound, deep pipeline still fits); for BN >= 128 the shallower
+  // smem ring and the single TMEM buffer cost more than the saved traffic (measured), so one tap per item there
+  int tmax = (bn <= 64) ? 512 / bn : 1; if (tmax > taps) tmax = taps;
+  p.groups = (taps + tmax - 1) / tmax;
+  p.taps_per_group = (taps + p.groups - 1) / p.groups;
+  p.nbuf = (2 * p.taps_per_group * bn <= 512) ? 2 : 1;
   p.m_rows = g.m_rows();
   p.kblocks_total = (int)((p.m_rows + 63) / 64);
   p.co_tiles = (cout + 127) / 128;
@@ -168,7 +187,7 @@ int wgrad_gemm_tc(const void* dy, long long dy_rows, int dy_ld, int cout, int dy
   p.taps = taps;
   for (int t = 0; t < 9; t++) p.shifts[t] = (taps == 9) ? ((t / 3) - 1) * g.Wp() + ((t % 3) - 1) : 0;
   p.cout = cout; p.cin = cin;
-  const int base_items = p.co_tiles * p.ci_tiles * taps;
+  const int base_items = p.co_tiles * p.ci_tiles * p.groups;
   // split K until there are ~2 waves of work items, keeping at least 32 k-blocks (2048 rows) per item
   int splits = (2 * g_num_sms_w + base_items - 1) / base_items;
   int max_splits = p.kblocks_total / 32; if (max_splits < 1) max_splits = 1;
@@ -176,7 +195,7 @@ int wgrad_gemm_tc(const void* dy, long long dy_rows, int dy_ld, int cout, int dy
   if (splits < 1) splits = 1;
   p.splits = splits;
   p.idesc = umma_idesc_f16(dy_fmt, x_fmt, 1, 1, bn);
-  p.stage_bytes = (2 + bn / 64) * kBox;
+  p.stage_bytes = (2 + p.taps_per_group * nb) * kBox;
   const int fixed = (2 * kMaxStagesW + 4) * 8 + 16 + 1024;
   int stages = (227 * 1024 - fixed) / p.stage_bytes;
   if (stages > kMaxStagesW) stages = kMaxStagesW;
