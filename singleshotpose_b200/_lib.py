@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libssp_b200.so")
 
 FMT_F16, FMT_BF16 = 0, 1
-IMPL_TC, IMPL_SIMT = 0, 1
+IMPL_TC, IMPL_SIMT, IMPL_TC2 = 0, 1, 2
 EPI_F32, EPI_STATS, EPI_BIAS = 0, 1, 2
 ROUTE_NONE, ROUTE_DIRECT, ROUTE_POOL, ROUTE_REORG = 0, 1, 2, 3
 

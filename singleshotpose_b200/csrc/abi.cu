@@ -14,6 +14,8 @@ int fail_msg(int code, const char* msg) { snprintf(g_err, sizeof(g_err), "%s", m
 
 int conv_gemm_tc(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
                  float*, int, long long, int, const float*, double*, double*, cudaStream_t);
+int conv_gemm_tc2(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
+                  float*, int, long long, int, const float*, double*, double*, cudaStream_t);
 int conv_gemm_simt(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
                    float*, int, long long, int, const float*, double*, double*, cudaStream_t);
 int wgrad_gemm_tc(const void*, long long, int, int, int, const void*, long long, int, int, int, int, int, int, int, float*, int, int, float, cudaStream_t);
@@ -60,6 +62,8 @@ int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo, long long a_rows
                   long long out_rows, int epi, const float* bias, double* ssum, double* ssq, void* s) {
   if (impl == SSP_IMPL_SIMT)
     return conv_gemm_simt(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
+  if (impl == SSP_IMPL_TC2)
+    return conv_gemm_tc2(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
   return conv_gemm_tc(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
 }
 int ssp_wgrad_gemm(int impl, const void* dy, long long dy_rows, int dy_ld, int cout, int dy_fmt, const void* x, long long x_rows, int x_ld,

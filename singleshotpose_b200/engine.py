@@ -155,9 +155,11 @@ class Engine:
         self._views = None
         self._buffers = {}
         self._weights_version = None
-        impl = os.environ.get("SSP_CONV_IMPL", "tc").lower()
-        self.conv_impl = _lib.IMPL_SIMT if impl == "simt" else _lib.IMPL_TC
-        wimpl = os.environ.get("SSP_WGRAD_IMPL", impl).lower()
+        impl = os.environ.get("SSP_CONV_IMPL", "auto").lower()
+        # "auto": CTA-pair kernel (cta_group::2) where the N tile is >= SSP_TC2_MIN_N wide, 1-CTA kernel for narrow layers
+        self.conv_impl = {"simt": _lib.IMPL_SIMT, "tc2": _lib.IMPL_TC2, "tc": _lib.IMPL_TC, "auto": -1}.get(impl, -1)
+        self.tc2_min_n = int(os.environ.get("SSP_TC2_MIN_N", "128"))
+        wimpl = os.environ.get("SSP_WGRAD_IMPL", "simt" if impl == "simt" else "tc").lower()
         self.wgrad_impl = _lib.IMPL_SIMT if wimpl == "simt" else _lib.IMPL_TC
         # backward operands: one 16-bit format for dY, W and X (tcgen05 kind::f16 cannot mix fp16 with bf16 -- illegal
         # instruction, measured).  fp16 + a static loss scale (saturating conversion) is 8x more precise than bf16.
@@ -274,6 +276,11 @@ class Engine:
             self._buffers[key] = b
         return b
 
+    def _conv_impl(self, n_out):
+        if self.conv_impl >= 0:
+            return self.conv_impl
+        return _lib.IMPL_TC2 if n_out >= self.tc2_min_n else _lib.IMPL_TC
+
     def _gemm(self, kind, L, N, h, w, name, *args):
         """launch one GEMM-shaped kernel; optionally bracket it with CUDA events on the launching stream (bench roofline)."""
         self.launches += 1
@@ -314,7 +321,7 @@ class Engine:
                 bias = None
             else:
                 epi, bias = _lib.EPI_BIAS, ptr(conv.bias.data)
-            self._gemm("fwd", L, N, h, w, "ssp_conv_gemm", self.conv_impl, ptr(xin), a_lo, B.rows[i], xin.shape[1], L.k_cin,
+            self._gemm("fwd", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cout), ptr(xin), a_lo, B.rows[i], xin.shape[1], L.k_cin,
                        ptr(self.w_hi[i]), b_lo, L.cout, self.w_hi[i].shape[1], _lib.FMT_F16, _lib.FMT_F16,
                        N, h, w, L.k_taps, L.cout, ptr(B.y[i]), B.y[i].shape[1], B.rows[i], epi, bias,
                        ptr(st["ssum"]), ptr(st["ssq"]), s)
@@ -381,6 +388,6 @@ class Engine:
                 self._gemm("wgrad", L, N, h, w, "ssp_wgrad_gemm", self.wgrad_impl, ptr(dy), B.rows[i], dy.shape[1], L.cout, self.grad_fmt,
                            ptr(xh), B.rows[i], xh.shape[1], L.cin, self.grad_fmt, N, h, w, L.taps, ptr(dw), L.cin, L.cin, inv, s)
                 wd = self.w_d[i]
-                self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm", self.conv_impl, ptr(dy), None, B.rows[i], dy.shape[1], L.cout, ptr(wd), None,
+                self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cin), ptr(dy), None, B.rows[i], dy.shape[1], L.cout, ptr(wd), None,
                            L.cin, wd.shape[1], self.grad_fmt, self.grad_fmt, N, h, w, L.taps, L.cin, ptr(B.dx[i]), B.dx[i].shape[1], B.rows[i],
                            _lib.EPI_F32, None, None, None, s)

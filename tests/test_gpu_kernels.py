@@ -78,7 +78,7 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("impl", [_lib.IMPL_SIMT, _lib.IMPL_TC])
+@pytest.mark.parametrize("impl", [_lib.IMPL_SIMT, _lib.IMPL_TC, _lib.IMPL_TC2])
 def test_conv_gemm_matches_torch(case, impl):
     N, H, W, cin, cout, k, use_bias = case
     g = torch.Generator().manual_seed(hash(case) % 1000)
@@ -116,7 +116,7 @@ def test_conv_gemm_single_term_bf16_dgrad_layout():
     w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
     dyq = dy.bfloat16().float(); wq = w.bfloat16().float()
     ref = F.conv_transpose2d(dyq.double(), wq.double(), padding=1).float()
-    for impl in (_lib.IMPL_SIMT, _lib.IMPL_TC):
+    for impl in (_lib.IMPL_SIMT, _lib.IMPL_TC, _lib.IMPL_TC2):
         dyh, _, rows = flat_from_nchw(dy.to(DEV), fmt=_lib.FMT_BF16, split=False)
         _, _, wd = _pack_w(w.to(DEV), fmt=_lib.FMT_BF16, dgrad=True)
         dx = torch.zeros(rows, cin, device=DEV)
