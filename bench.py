@@ -171,7 +171,9 @@ def main():
     model = Darknet(write_cfg()).to(dev).train()
     crit = RegionLoss(); crit.verbose = False
     gb = B * world
-    opt = FlatSGD(model, lr=0.001 * 0.1 / gb, momentum=0.9, weight_decay=0.0005 * gb)      # train.py:388 + lr schedule :34-46
+    from singleshotpose_b200.optim import dp_hyperparams
+    lr, wd = dp_hyperparams(0.001 * 0.1, 0.0005, B)                                          # train.py:388 + lr schedule :34-46
+    opt = FlatSGD(model, lr=lr, momentum=0.9, weight_decay=wd)
     x_host = synth.images(B, seed=100 + rank).pin_memory()
     t_host = synth.targets(B, seed=200 + rank).pin_memory()
     x_dev, t_dev = x_host.to(dev), t_host.to(dev)

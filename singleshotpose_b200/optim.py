@@ -8,6 +8,23 @@ import torch
 from ._lib import call, ptr, stream_ptr
 
 
+def all_reduce_flat_(flat):
+    """SUM all-reduce of the flat gradient buffer over the data-parallel group (NCCL on GPUs, gloo in the CPU tests).
+    The loss is a SUM over images (region_loss.py:149-161), so gradients add across ranks."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return flat
+
+
+def dp_hyperparams(learning_rate, decay, per_gpu_batch):
+    """train.py:388 divides lr and multiplies weight decay by the batch size: with data parallelism that is the GLOBAL batch."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    gb = per_gpu_batch * world
+    return learning_rate / gb, decay * gb
+
+
 class FlatSGD:
     def __init__(self, model, lr, momentum=0.0, weight_decay=0.0):
         self.model = model
@@ -19,9 +36,7 @@ class FlatSGD:
             p.grad = None
 
     def all_reduce_grads(self):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.model._engine.flat_grads, op=dist.ReduceOp.SUM)
+        all_reduce_flat_(self.model._engine.flat_grads)
 
     def step(self, grad_scale=1.0):
         eng = self.model._engine
