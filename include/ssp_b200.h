@@ -103,6 +103,19 @@ int ssp_region_decode_argmax(const float* out_nchw, int B, int num_keypoints, in
                              int only_objectness, float* boxes, float* best_conf, float* box_global_or_null,
                              void* stream);
 
+/* ---- multi-object head (multi_obj_pose_estimation/region_loss_multi.py:9-189, utils_multi.py:266-382).
+ *      `anchors` is a HOST array of num_anchors*anchor_step floats; acc[6] additionally holds loss_cls.
+ *      decode: dense per (image, cell, anchor) arrays in the reference's visiting order + its sequential fallback maxima ---- */
+int ssp_region_loss_multi_fwd_bwd(const float* out_nchw, const float* target, float* grad_nchw_or_null, double* acc,
+                                  int B, int num_keypoints, int num_classes, int num_anchors, int H, int W,
+                                  const float* anchors_host, int anchor_step, float coord_scale, float noobject_scale,
+                                  float object_scale, float class_scale, float thresh, int use_conf, float grad_scale,
+                                  void* stream);
+int ssp_region_decode_multi(const float* out_nchw, int B, int num_keypoints, int num_classes, int num_anchors, int H,
+                            int W, int only_objectness, int correspondingclass, float* boxes, float* conf_sel,
+                            float* det_conf, float* cls_corr, long long* max_ind, float* max_conf, float* max_cls,
+                            void* stream);
+
 /* ---- pnp (utils.py:86-100 -> cv2.solvePnP ITERATIVE + Rodrigues), compute_projection (utils.py:40-45) ---- */
 int ssp_pnp_batched(const float* points3d, int points3d_shared, const float* points2d, const float* K3x3,
                     int num_points, long long n, int max_iter, double* R_out, double* t_out,

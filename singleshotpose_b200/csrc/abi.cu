@@ -36,6 +36,9 @@ int pack_weights(const float*, int, int, int, void*, void*, int, void*, int, int
 int sgd_step_flat(float*, const float*, float*, long long, float, float, float, float, cudaStream_t);
 int region_loss_fwd_bwd(const float*, const float*, float*, double*, int, int, int, int, int, float, float, float, float, int, float, cudaStream_t);
 int region_decode_argmax(const float*, int, int, int, int, int, int, float*, float*, float*, cudaStream_t);
+int region_loss_multi_fwd_bwd(const float*, const float*, float*, double*, int, int, int, int, int, int, const float*, int, float, float, float,
+                              float, float, int, float, cudaStream_t);
+int region_decode_multi(const float*, int, int, int, int, int, int, int, int, float*, float*, float*, float*, long long*, float*, float*, cudaStream_t);
 int pnp_batched(const float*, int, const float*, const float*, int, long long, int, double*, double*, int*, cudaStream_t);
 int project_points(const float*, int, int, const double*, const double*, long long, float*, cudaStream_t);
 }  // namespace ssp
@@ -101,6 +104,16 @@ int ssp_region_loss_fwd_bwd(const float* out, const float* target, float* grad, 
 }
 int ssp_region_decode_argmax(const float* out, int B, int K, int nC, int H, int W, int only_objectness, float* boxes, float* best_conf, float* box_global, void* s) {
   return region_decode_argmax(out, B, K, nC, H, W, only_objectness, boxes, best_conf, box_global, ST(s));
+}
+int ssp_region_loss_multi_fwd_bwd(const float* out, const float* target, float* grad, double* acc, int B, int K, int nC, int nA, int H, int W,
+                                  const float* anchors_host, int anchor_step, float coord_scale, float noobject_scale, float object_scale,
+                                  float class_scale, float thresh, int use_conf, float grad_scale, void* s) {
+  return region_loss_multi_fwd_bwd(out, target, grad, acc, B, K, nC, nA, H, W, anchors_host, anchor_step, coord_scale, noobject_scale, object_scale,
+                                   class_scale, thresh, use_conf, grad_scale, ST(s));
+}
+int ssp_region_decode_multi(const float* out, int B, int K, int nC, int nA, int H, int W, int only_objectness, int corr, float* boxes, float* conf_sel,
+                            float* det, float* cls_corr, long long* max_ind, float* max_conf, float* max_cls, void* s) {
+  return region_decode_multi(out, B, K, nC, nA, H, W, only_objectness, corr, boxes, conf_sel, det, cls_corr, max_ind, max_conf, max_cls, ST(s));
 }
 int ssp_pnp_batched(const float* P3, int shared, const float* uv, const float* K, int np, long long n, int max_iter, double* R, double* t, int* iters, void* s) {
   return pnp_batched(P3, shared, uv, K, np, n, max_iter, R, t, iters, ST(s));

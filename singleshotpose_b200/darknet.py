@@ -57,6 +57,8 @@ class _DarknetFn(torch.autograd.Function):
 
 
 class Darknet(nn.Module):
+    _region_loss_cls = None        # darknet_multi.Darknet overrides this with the multi-object head
+
     def __init__(self, cfgfile):
         super().__init__()
         self.blocks = parse_cfg(cfgfile)
@@ -68,6 +70,7 @@ class Darknet(nn.Module):
         self.test_width = int(net.get("test_width", net["width"]))
         self.test_height = int(net.get("test_height", net["height"]))
         self.num_keypoints = int(net.get("num_keypoints", 9))
+        self.loss.num_keypoints = self.num_keypoints if hasattr(self.loss, "num_keypoints") else None
         if self.blocks[-1]["type"] == "region":
             self.anchors = self.loss.anchors
             self.num_anchors = self.loss.num_anchors
@@ -80,7 +83,8 @@ class Darknet(nn.Module):
 
     # ---- construction: same module order / ctor args as darknet.py:135-249 so that seeded init is identical ----
     def create_network(self, blocks):
-        from .region_loss import RegionLoss
+        from .region_loss import RegionLoss as _SingleLoss
+        RegionLoss = self._region_loss_cls or _SingleLoss
         models = nn.ModuleList()
         prev_filters = 3
         out_filters = []

@@ -30,6 +30,27 @@ def targets(batch, seed=1, num_keypoints=9, max_objs=50):
     return torch.from_numpy(t)
 
 
+def targets_multi(batch, seed=1, num_keypoints=9, max_objs=50, num_classes=13, min_objs=1, max_gts=3):
+    """(batch, 50*21) float32 with 1..max_gts objects per image: class U{0..12}, centroid U(.1,.9),
+    corners = centroid + U(-.15,.15), x/y range U(0.05, 0.4) (drives the anchor choice)."""
+    rng = np.random.default_rng(seed)
+    nl = 2 * num_keypoints + 3
+    t = np.zeros((batch, max_objs * nl), np.float32)
+    for b in range(batch):
+        for k in range(int(rng.integers(min_objs, max_gts + 1))):
+            c = rng.uniform(0.1, 0.9, size=2)
+            pts = np.concatenate([c[None], c[None] + rng.uniform(-0.15, 0.15, size=(num_keypoints - 1, 2))])
+            o = k * nl
+            t[b, o] = rng.integers(0, num_classes)
+            t[b, o + 1:o + 1 + 2 * num_keypoints] = pts.reshape(-1)
+            t[b, o + 1 + 2 * num_keypoints] = rng.uniform(0.05, 0.4)
+            t[b, o + 2 + 2 * num_keypoints] = rng.uniform(0.05, 0.4)
+    return torch.from_numpy(t)
+
+
+MULTI_ANCHORS = [1.4820, 2.2412, 2.0501, 3.1265, 2.3946, 4.6891, 3.1018, 3.9910, 3.4879, 5.8851]   # yolo-pose-multi.cfg:240
+
+
 def intrinsics(dtype=np.float64):
     k = LINEMOD_INTRINSICS
     return np.array([[k["fx"], 0.0, k["u0"]], [0.0, k["fy"], k["v0"]], [0.0, 0.0, 1.0]], dtype)

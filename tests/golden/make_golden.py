@@ -175,5 +175,68 @@ def main():
     np.savez_compressed(os.path.join(HERE, "pnp.npz"), P3=pr["P3"], K=pr["K"], **res)
 
 
+def main_multi():
+    """multi-object head: reference build_targets / bbox_iou / get_multi_region_boxes vs the restatements."""
+    from oracle import region_loss_multi_ref as RM
+    from oracle.decode_multi_ref import get_multi_region_boxes_ref
+    mdir = os.path.join(REF, "multi_obj_pose_estimation")
+    sys.path.insert(0, mdir)
+    cwd = os.getcwd(); os.chdir(mdir)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import region_loss_multi as ref_rlm
+        import utils_multi as ref_um
+    os.chdir(cwd)
+    A = synth.MULTI_ANCHORS
+    g = torch.Generator().manual_seed(13)
+    B = 5
+    out = torch.randn(B, 160, 13, 13, generator=g) * 0.7
+    tgt = synth.targets_multi(B, seed=14)
+    tgt[1, 21:] = 0                                     # image 1: exactly one object
+    tgt[3, 21 + 1:21 + 3] = tgt[3, 1:3]                 # image 3: two objects with the same centroid cell
+    tgt[3, 21 + 19:21 + 21] = tgt[3, 19:21]             #          and the same extent => same anchor: later GT overwrites
+    res = {}
+    for epoch in (0, 20):
+        o = out.clone().requires_grad_(True)
+        loss, info = RM.region_loss_multi_ref(o, tgt, epoch, A, build_targets=lambda *a: ref_rlm.build_targets(*a, 0))
+        loss.backward()
+        o2 = out.clone().requires_grad_(True)
+        loss2, info2 = RM.region_loss_multi_ref(o2, tgt, epoch, A)
+        loss2.backward()
+        assert torch.equal(loss, loss2) and torch.equal(o.grad, o2.grad), "restated multi build_targets differs"
+        for k in ("tconf", "conf_mask", "coord_mask", "tcls"):
+            assert torch.equal(info[k], info2[k]), k
+        res["loss_e%d" % epoch] = float(loss); res["grad_e%d" % epoch] = o.grad.numpy().copy()
+        res["parts_e%d" % epoch] = np.array([float(info[k]) for k in ("loss_x", "loss_y", "loss_conf", "loss_cls")])
+        res["counters_e%d" % epoch] = np.array([info["nGT"], info["nCorrect"], info["nProposals"]])
+    assert ref_um.bbox_iou([0, 0, 2.0, 3.0], [0, 0, 1.5, 4.0], x1y1x2y2=False) == RM.bbox_iou_ref([0, 0, 2.0, 3.0], [0, 0, 1.5, 4.0])
+    np.savez_compressed(os.path.join(HERE, "region_loss_multi.npz"), output=out.numpy(), target=tgt.numpy(), anchors=np.array(A), **res)
+    print("multi region golden:", {k: v for k, v in res.items() if k.startswith(("loss", "counters"))})
+    # decode
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref_boxes = ref_um.get_multi_region_boxes(out.clone() * 3, 0.05, 13, 9, A, 5, 4, only_objectness=0)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    ora_boxes = get_multi_region_boxes_ref(out.clone() * 3, 0.05, 13, 9, A, 5, 4, only_objectness=0)
+    assert len(ref_boxes) == len(ora_boxes)
+    flat, counts = [], []
+    for rb, ob in zip(ref_boxes, ora_boxes):
+        assert len(rb) == len(ob), (len(rb), len(ob))
+        for r1, o1 in zip(rb, ob):
+            a1 = np.array([float(v) for v in r1]); a2 = np.array([float(v) for v in o1])
+            assert np.array_equal(a1, a2)
+            flat.append(a1[:21])
+        counts.append(len(rb))
+    np.savez_compressed(os.path.join(HERE, "decode_multi.npz"), output=(out * 3).numpy(), boxes=np.array(flat), counts=np.array(counts),
+                        anchors=np.array(A), conf_thresh=0.05, correspondingclass=4)
+    print("multi decode golden: boxes per image", counts)
+
+
 if __name__ == "__main__":
-    main()
+    if "--multi-only" not in sys.argv:
+        main()
+    main_multi()
