@@ -4,4 +4,5 @@ reference's Python surface (Darknet, RegionLoss, get_region_boxes, pnp)."""
 from .darknet import Darknet          # noqa: F401
 from .region_loss import RegionLoss   # noqa: F401
 from .optim import FlatSGD            # noqa: F401
+from .graph import GraphedTrainStep   # noqa: F401
 from . import utils, utils_multi, cfg, cfgs, synth, darknet_multi, region_loss_multi  # noqa: F401

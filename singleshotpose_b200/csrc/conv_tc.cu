@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; j++) if (c0 + j < p.cout) v[j] += __ldg(p.bias + c0 + j);
         }
-        if (can_store) {
+        if (can_store && p.epi != 3) {     // epi 3: diagnostic mode without the global store
           if (c0 + 32 <= p.cout) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
