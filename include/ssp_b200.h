@@ -60,6 +60,10 @@ int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo_or_null, long lon
                   const void* b_hi, const void* b_lo_or_null, int b_rows, int b_ld, int a_fmt, int b_fmt,
                   int N, int H, int W, int taps, int cout, float* out, int out_ld, long long out_rows, int epi,
                   const float* bias, double* stat_sum, double* stat_sq, void* stream);
+/* ---- first layer nn.Conv2d(3, 32, 3, 1, 1) (darknet.py:156, block 0): direct fp32 convolution of the NCHW image with the
+ *      fp32 master weights [32][3][3][3] (k = (kh*3+kw)*3 + ci), output rows [row(n,h,w)][y_ld], optional fp64 BN statistics ---- */
+int ssp_conv0_direct(const float* x_nchw, const float* w, const float* bias_or_null, float* y, int y_ld,
+                     double* stat_sum_or_null, double* stat_sq_or_null, int N, int H, int W, void* stream);
 /* ---- nn.Conv2d weight gradient: dW[co][tap][ci] += scale * sum_m dY[m][co] * X[m + shift(tap)][ci] ---- */
 int ssp_wgrad_gemm(int impl, const void* dy, long long dy_rows, int dy_ld, int cout, int dy_fmt, const void* x,
                    long long x_rows, int x_ld, int cin, int x_fmt, int N, int H, int W, int taps, float* dw,

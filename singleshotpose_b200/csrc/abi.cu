@@ -18,6 +18,7 @@ int conv_gemm_tc2(const void*, const void*, long long, int, int, const void*, co
                   float*, int, long long, int, const float*, double*, double*, cudaStream_t);
 int conv_gemm_simt(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
                    float*, int, long long, int, const float*, double*, double*, cudaStream_t);
+int conv0_direct(const float*, const float*, const float*, float*, int, double*, double*, int, int, int, cudaStream_t);
 int wgrad_gemm_tc(const void*, long long, int, int, int, const void*, long long, int, int, int, int, int, int, int, float*, int, int, float, cudaStream_t);
 int wgrad_gemm_simt(const void*, long long, int, int, int, const void*, long long, int, int, int, int, int, int, int, float*, int, int, float, cudaStream_t);
 int pack_input_im2col(const float*, void*, void*, int, int, int, cudaStream_t);
@@ -68,6 +69,9 @@ int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo, long long a_rows
   if (impl == SSP_IMPL_TC2)
     return conv_gemm_tc2(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
   return conv_gemm_tc(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
+}
+int ssp_conv0_direct(const float* x, const float* w, const float* bias, float* y, int y_ld, double* ssum, double* ssq, int N, int H, int W, void* s) {
+  return conv0_direct(x, w, bias, y, y_ld, ssum, ssq, N, H, W, ST(s));
 }
 int ssp_wgrad_gemm(int impl, const void* dy, long long dy_rows, int dy_ld, int cout, int dy_fmt, const void* x, long long x_rows, int x_ld,
                    int cin, int x_fmt, int N, int H, int W, int taps, float* dw, int dw_ld, int cin_store, float scale, void* s) {

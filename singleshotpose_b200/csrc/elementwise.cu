@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) pack_input_im2col_kernel(const float* __r
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     dh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-    dl[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+    if (lo) dl[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
   }
 }
 
@@ -493,7 +493,7 @@ __global__ void sgd_flat_kernel(float* __restrict__ p, const float* __restrict__
 static inline unsigned nblk(long long total, int bs) { return (unsigned)((total + bs - 1) / bs); }
 
 int pack_input_im2col(const float* x, void* hi, void* lo, int N, int H, int W, cudaStream_t s) {
-  if (!x || !hi || !lo) return fail_msg(SSP_ERR_ARG, "pack_input_im2col: null pointer");
+  if (!x || !hi) return fail_msg(SSP_ERR_ARG, "pack_input_im2col: null pointer");
   const long long total = (long long)N * H * W;
   pack_input_im2col_kernel<<<nblk(total, 256), 256, 0, s>>>(x, (uint16_t*)hi, (uint16_t*)lo, N, H, W);
   SSP_CHECK_LAUNCH(); return SSP_OK;

@@ -293,6 +293,13 @@ class Engine:
         e1.record()
         self.profile.append((kind, L.block_ind, 2.0 * N * h * w * L.cout * L.cin * L.taps, e0, e1))
 
+    def _conv_fwd(self, L, B, N, h, w, xin, a_lo, b_lo, epi, bias, st, s):
+        i = L.index
+        self._gemm("fwd", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cout), ptr(xin), a_lo, B.rows[i], xin.shape[1], L.k_cin,
+                   ptr(self.w_hi[i]), b_lo, L.cout, self.w_hi[i].shape[1], _lib.FMT_F16, _lib.FMT_F16,
+                   N, h, w, L.k_taps, L.cout, ptr(B.y[i]), B.y[i].shape[1], B.rows[i], epi, bias,
+                   ptr(st["ssum"]), ptr(st["ssq"]), s)
+
     # ------------------------------------------------------------------ forward
     def forward(self, x, train_bn, keep_for_backward):
         """x: (N,3,H,W) fp32 CUDA -> logits (N,Cout,h,w) fp32.  train_bn: batch statistics + running-stat update."""
@@ -306,8 +313,10 @@ class Engine:
         B.generation += 1
         s = stream_ptr()
         mods = self.conv_modules()
-        call("ssp_pack_input_im2col", ptr(x), ptr(B.x_hi[0]), ptr(B.x_lo[0]), N, H, W, s)
-        self.launches += 1
+        direct0 = self.conv_impl != _lib.IMPL_SIMT and not self.fast and os.environ.get("SSP_L0", "direct") == "direct"
+        if not direct0 or keep_for_backward:       # the im2col'ed plane feeds the tensor-core GEMMs (forward unless direct, wgrad always)
+            call("ssp_pack_input_im2col", ptr(x), ptr(B.x_hi[0]), None if direct0 else ptr(B.x_lo[0]), N, H, W, s)
+            self.launches += 1
         for L in self.layers:
             i = L.index
             conv, bn = mods[i]
@@ -321,10 +330,13 @@ class Engine:
                 bias = None
             else:
                 epi, bias = _lib.EPI_BIAS, ptr(conv.bias.data)
-            self._gemm("fwd", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cout), ptr(xin), a_lo, B.rows[i], xin.shape[1], L.k_cin,
-                       ptr(self.w_hi[i]), b_lo, L.cout, self.w_hi[i].shape[1], _lib.FMT_F16, _lib.FMT_F16,
-                       N, h, w, L.k_taps, L.cout, ptr(B.y[i]), B.y[i].shape[1], B.rows[i], epi, bias,
-                       ptr(st["ssum"]), ptr(st["ssq"]), s)
+            if L.first and direct0 and L.bn:       # exact fp32 direct convolution of the raw image (HBM-bound layer)
+                off, n, _gv = self._slices[id(conv.weight)]
+                call("ssp_conv0_direct", ptr(x), ptr(self.flat_params[off:off + n]), None, ptr(B.y[i]), B.y[i].shape[1],
+                     ptr(st["ssum"]) if train_bn else None, ptr(st["ssq"]) if train_bn else None, N, H, W, s)
+                self.launches += 1
+            else:
+                self._conv_fwd(L, B, N, h, w, xin, a_lo, b_lo, epi, bias, st, s)
             if not L.bn:
                 continue
             call("ssp_bn_finalize", ptr(st["ssum"]), ptr(st["ssq"]), float(N * h * w), ptr(bn.weight.data), ptr(bn.bias.data),
