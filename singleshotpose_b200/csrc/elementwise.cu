@@ -269,8 +269,9 @@ __device__ __forceinline__ BwdConsts bwd_consts(const BnBwdParams& p, int c) {
 }
 
 // one unit (pixel or 2x2 window) of the backward pass: all global loads first, arithmetic afterwards
-template <bool POOLED>
+template <int K0, int K1>
 struct BwdUnit {
+  static constexpr bool POOLED = (K0 == SRC_POOL || K1 == SRC_POOL);
   static constexpr int NP = POOLED ? 4 : 1;
   float4 y[NP], gd[2][NP], gp[2];
   long long rows[NP];
@@ -290,16 +291,18 @@ struct BwdUnit {
 #pragma unroll
       for (int s = 0; s < 2; s++) {
         const GradSrc& gs = p.src[s];
+        const int kind = s == 0 ? K0 : K1;                 // compile-time: unused sources cost no registers
         gd[s][q] = make_float4(0, 0, 0, 0);
-        if (gs.kind == SRC_DIRECT) gd[s][q] = *reinterpret_cast<const float4*>(gs.g + rows[q] * gs.ld + gs.c0 + c);
-        else if (gs.kind == SRC_REORG)
+        if (kind == SRC_DIRECT) gd[s][q] = *reinterpret_cast<const float4*>(gs.g + rows[q] * gs.ld + gs.c0 + c);
+        else if (kind == SRC_REORG)
           gd[s][q] = *reinterpret_cast<const float4*>(gs.g + gh.row(n, h >> 1, w >> 1) * gs.ld + gs.c0 + ((h & 1) * 2 + (w & 1)) * p.C + c);
       }
     }
 #pragma unroll
     for (int s = 0; s < 2; s++) {
+      const int kind = s == 0 ? K0 : K1;
       gp[s] = make_float4(0, 0, 0, 0);
-      if (POOLED && p.src[s].kind == SRC_POOL)
+      if (kind == SRC_POOL)
         gp[s] = *reinterpret_cast<const float4*>(p.src[s].g + gh.row(n, hs, ws) * p.src[s].ld + p.src[s].c0 + c);
     }
   }
@@ -337,9 +340,10 @@ struct BwdUnit {
 
 #define BWD_REDUCE_UNITS_PER_THREAD 32
 
-template <bool POOLED>
+template <int K0, int K1>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
   extern __shared__ float red[];           // [2][PL][CG*4]
+  constexpr bool POOLED = BwdUnit<K0, K1>::POOLED;
   const int Hs = POOLED ? p.H / 2 : p.H, Ws = POOLED ? p.W / 2 : p.W;
   UnitWalk wk(p.C, (long long)p.N * Hs * Ws, BWD_REDUCE_UNITS_PER_THREAD);
   constexpr int NP = POOLED ? 4 : 1;
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
   if (wk.active) {
     const BwdConsts k = bwd_consts(p, c);
     for (long long u0 = wk.begin + wk.pl; u0 < wk.end; u0 += (long long)UNR * wk.PL) {
-      BwdUnit<POOLED> un[UNR];
+      BwdUnit<K0, K1> un[UNR];
 #pragma unroll
       for (int t = 0; t < UNR; t++) un[t].load(p, u0 + (long long)t * wk.PL, wk.begin, wk.end, Hs, Ws, c);
 #pragma unroll
@@ -381,8 +385,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
   }
 }
 
-template <bool POOLED>
+template <int K0, int K1>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
+  constexpr bool POOLED = BwdUnit<K0, K1>::POOLED;
   const int Hs = POOLED ? p.H / 2 : p.H, Ws = POOLED ? p.W / 2 : p.W;
   UnitWalk wk(p.C, (long long)p.N * Hs * Ws, BN_UNITS_PER_THREAD);
   if (!wk.active) return;
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
     for (int j = 0; j < 4; j++) gsc[j] = p.dy_scale;
   }
   for (long long u0 = wk.begin + wk.pl; u0 < wk.end; u0 += (long long)UNR * wk.PL) {
-    BwdUnit<POOLED> un[UNR];
+    BwdUnit<K0, K1> un[UNR];
 #pragma unroll
     for (int t = 0; t < UNR; t++) un[t].load(p, u0 + (long long)t * wk.PL, wk.begin, wk.end, Hs, Ws, c);
 #pragma unroll
@@ -565,8 +570,20 @@ int bn_bwd_reduce(const float* y, int y_ld, const float* scale, const float* shi
   const long long nunits = (long long)N * (pooled ? H / 2 : H) * (pooled ? W / 2 : W);
   const size_t sm = (size_t)2 * PL * CG * 4 * sizeof(float);
   const unsigned grid = unit_grid(C, nunits, BWD_REDUCE_UNITS_PER_THREAD);
-  if (pooled) bn_bwd_reduce_kernel<true><<<grid, 256, sm, s>>>(p);
-  else bn_bwd_reduce_kernel<false><<<grid, 256, sm, s>>>(p);
+#define SSP_BWD_DISPATCH(KERN, ...)                                                                                  \
+  do {                                                                                                              \
+    const int k0 = p.src[0].kind, k1 = p.src[1].kind;                                                               \
+    if (k0 == SRC_DIRECT && k1 == SRC_NONE) KERN<SRC_DIRECT, SRC_NONE><<<__VA_ARGS__>>>(p);                         \
+    else if (k0 == SRC_POOL && k1 == SRC_NONE) KERN<SRC_POOL, SRC_NONE><<<__VA_ARGS__>>>(p);                        \
+    else if (k0 == SRC_REORG && k1 == SRC_NONE) KERN<SRC_REORG, SRC_NONE><<<__VA_ARGS__>>>(p);                      \
+    else if (k0 == SRC_POOL && k1 == SRC_DIRECT) KERN<SRC_POOL, SRC_DIRECT><<<__VA_ARGS__>>>(p);                    \
+    else if (k0 == SRC_DIRECT && k1 == SRC_POOL) KERN<SRC_DIRECT, SRC_POOL><<<__VA_ARGS__>>>(p);                    \
+    else if (k0 == SRC_DIRECT && k1 == SRC_DIRECT) KERN<SRC_DIRECT, SRC_DIRECT><<<__VA_ARGS__>>>(p);                \
+    else if (k0 == SRC_DIRECT && k1 == SRC_REORG) KERN<SRC_DIRECT, SRC_REORG><<<__VA_ARGS__>>>(p);                  \
+    else if (k0 == SRC_REORG && k1 == SRC_DIRECT) KERN<SRC_REORG, SRC_DIRECT><<<__VA_ARGS__>>>(p);                  \
+    else return fail_msg(SSP_ERR_ARG, "bn_bwd: unsupported combination of gradient routes");                         \
+  } while (0)
+  SSP_BWD_DISPATCH(bn_bwd_reduce_kernel, grid, 256, sm, s);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
 int bn_bwd_apply(const float* y, int y_ld, const float* scale, const float* shift, const float* mean, const float* invstd,
@@ -581,8 +598,7 @@ int bn_bwd_apply(const float* y, int y_ld, const float* scale, const float* shif
   const bool pooled = p.src[0].kind == SRC_POOL || p.src[1].kind == SRC_POOL;
   const long long nunits = (long long)N * (pooled ? H / 2 : H) * (pooled ? W / 2 : W);
   const unsigned grid = unit_grid(C, nunits, BN_UNITS_PER_THREAD);
-  if (pooled) bn_bwd_apply_kernel<true><<<grid, 256, 0, s>>>(p);
-  else bn_bwd_apply_kernel<false><<<grid, 256, 0, s>>>(p);
+  SSP_BWD_DISPATCH(bn_bwd_apply_kernel, grid, 256, 0, s);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
 int bn_bwd_finalize(double* s1, double* s2, float* dgamma, float* dbeta, int C, int accumulate, float scale, cudaStream_t s) {
