@@ -169,6 +169,8 @@ class Engine:
         self.grad_dtype = torch.float16 if self.grad_fmt == _lib.FMT_F16 else torch.bfloat16
         self.fast = os.environ.get("SSP_PRECISION", "parity").lower() == "fast"   # single-term forward (no hi/lo)
         self.launches = 0
+        self.overlap = os.environ.get("SSP_OVERLAP", "1") != "0"
+        self._side = None
         self.profile = None          # set to [] to record (kind, layer block, algorithmic flops, start event, end event) per GEMM launch
         net = model.blocks[0]
         self.base_hw = (int(net["height"]), int(net["width"]))
@@ -281,16 +283,16 @@ class Engine:
             return self.conv_impl
         return _lib.IMPL_TC2 if n_out >= self.tc2_min_n else _lib.IMPL_TC
 
-    def _gemm(self, kind, L, N, h, w, name, *args):
+    def _gemm(self, kind, L, N, h, w, name, *args, stream=None):
         """launch one GEMM-shaped kernel; optionally bracket it with CUDA events on the launching stream (bench roofline)."""
         self.launches += 1
         if self.profile is None:
             call(name, *args)
             return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(stream)
         call(name, *args)
-        e1.record()
+        e1.record(stream)
         self.profile.append((kind, L.block_ind, 2.0 * N * h * w * L.cout * L.cin * L.taps, e0, e1))
 
     def _conv_fwd(self, L, B, N, h, w, xin, a_lo, b_lo, epi, bias, st, s):
@@ -366,6 +368,18 @@ class Engine:
         mods = self.conv_modules()
         self.flat_grads.zero_()
         g = grad_out.contiguous().float()
+        # Weight-gradient GEMMs (tensor/L2 bound) run on a side stream so that they overlap the HBM-bound BN-backward
+        # kernels of the next layer on the main stream; joined before returning.  Serial when per-launch profiling is on.
+        overlap = self.overlap and self.profile is None
+        main = torch.cuda.current_stream()
+        if overlap:
+            if self._side is None or self._side.device != main.device:
+                self._side = torch.cuda.Stream(device=main.device)
+            side = self._side
+            side.wait_stream(main)
+            ws, wstream = _lib.C.c_void_p(side.cuda_stream), side
+        else:
+            ws, wstream = s, None
         inv = 1.0 / self.grad_scale        # the whole backward chain carries the loss scale; undone where grads are written
         for L in reversed(self.layers):
             i = L.index
@@ -393,13 +407,21 @@ class Engine:
             off, n, _gv = self._slices[id(conv.weight)]
             dw = self.flat_grads[off:off + n]
             xh = B.x_hi[i]
-            if L.first:
-                self._gemm("wgrad", L, N, h, w, "ssp_wgrad_gemm", self.wgrad_impl, ptr(dy), B.rows[i], dy.shape[1], L.cout, self.grad_fmt,
-                           ptr(xh), B.rows[i], xh.shape[1], 32, self.grad_fmt, N, h, w, 1, ptr(dw), 27, 27, inv, s)
-            else:
-                self._gemm("wgrad", L, N, h, w, "ssp_wgrad_gemm", self.wgrad_impl, ptr(dy), B.rows[i], dy.shape[1], L.cout, self.grad_fmt,
-                           ptr(xh), B.rows[i], xh.shape[1], L.cin, self.grad_fmt, N, h, w, L.taps, ptr(dw), L.cin, L.cin, inv, s)
+            if overlap:
+                ev = torch.cuda.Event()
+                ev.record(main)                      # dY of this layer is complete
+            if not L.first:                          # data gradient first: it is on the critical path of the next layer
                 wd = self.w_d[i]
                 self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cin), ptr(dy), None, B.rows[i], dy.shape[1], L.cout, ptr(wd), None,
                            L.cin, wd.shape[1], self.grad_fmt, self.grad_fmt, N, h, w, L.taps, L.cin, ptr(B.dx[i]), B.dx[i].shape[1], B.rows[i],
                            _lib.EPI_F32, None, None, None, s)
+            if overlap:
+                side.wait_event(ev)
+            if L.first:
+                self._gemm("wgrad", L, N, h, w, "ssp_wgrad_gemm", self.wgrad_impl, ptr(dy), B.rows[i], dy.shape[1], L.cout, self.grad_fmt,
+                           ptr(xh), B.rows[i], xh.shape[1], 32, self.grad_fmt, N, h, w, 1, ptr(dw), 27, 27, inv, ws, stream=wstream)
+            else:
+                self._gemm("wgrad", L, N, h, w, "ssp_wgrad_gemm", self.wgrad_impl, ptr(dy), B.rows[i], dy.shape[1], L.cout, self.grad_fmt,
+                           ptr(xh), B.rows[i], xh.shape[1], L.cin, self.grad_fmt, N, h, w, L.taps, ptr(dw), L.cin, L.cin, inv, ws, stream=wstream)
+        if overlap:
+            main.wait_stream(side)
