@@ -32,6 +32,7 @@ extern "C" {
 #define SSP_FMT_BF16 1
 #define SSP_IMPL_TC 0    /* tcgen05 tensor-core kernel */
 #define SSP_IMPL_SIMT 1  /* fp32 CUDA-core kernel (cross-check / bring-up) */
+#define SSP_IMPL_BAND 3  /* narrow 3x3 layers: one activation band per kernel row + resident weights (falls back to TC) */
 #define SSP_IMPL_TC2 2   /* tcgen05 cta_group::2 kernel: CTA pairs share the weight tile (ssp_conv_gemm only) */
 #define SSP_EPI_F32 0    /* store fp32 */
 #define SSP_EPI_STATS 1  /* store fp32 + per-channel sum / sum of squares over valid pixels (fp64) */

@@ -6,10 +6,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libssp_b200.so")
+LIB_PATH = os.environ.get("SSP_LIB") or os.path.join(_HERE, "csrc", "libssp_b200.so")   # SSP_LIB: A/B experiments only
 
 FMT_F16, FMT_BF16 = 0, 1
-IMPL_TC, IMPL_SIMT, IMPL_TC2 = 0, 1, 2
+IMPL_TC, IMPL_SIMT, IMPL_TC2, IMPL_BAND = 0, 1, 2, 3
 EPI_F32, EPI_STATS, EPI_BIAS = 0, 1, 2
 ROUTE_NONE, ROUTE_DIRECT, ROUTE_POOL, ROUTE_REORG = 0, 1, 2, 3
 

@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["abi.cu", "conv_tc.cu", "conv_tc2.cu", "wgrad_tc.cu", "conv_simt.cu", "conv0_direct.cu", "elementwise.cu", "region.cu", "region_multi.cu", "pnp.cu"]
+SOURCES = ["abi.cu", "conv_tc.cu", "conv_tc2.cu", "conv_band.cu", "wgrad_tc.cu", "conv_simt.cu", "conv0_direct.cu", "elementwise.cu", "region.cu", "region_multi.cu", "pnp.cu"]
 LIB = os.path.join(HERE, "libssp_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -110,6 +110,20 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+// One lane of a CONVERGED warp.  The role loops run with the whole warp converged and only the MMA / TMA issue itself
+// under this predicate: operands then live in uniform registers (UTCHMMA / UTMALDG take UR operands); issuing from a
+// lane-divergent region makes the compiler wrap every instruction in an ELECT / R2UR.BROADCAST retry loop (~10 extra
+// instructions per MMA, which made N <= 128 layers issue-bound).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// SWIZZLE_128B K-major descriptor from its two 32-bit halves: hi is constant (SBO = 1024 B, version 1, layout 2)
+#define SSP_DESC_HI_SW128 0x40004040u
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  return ((uint64_t)SSP_DESC_HI_SW128 << 32) | (uint64_t)(((smem_addr >> 4) & 0x3FFFu) | 0x10000u);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {

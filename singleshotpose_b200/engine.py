@@ -159,6 +159,7 @@ class Engine:
         # "auto": CTA-pair kernel (cta_group::2) where the N tile is >= SSP_TC2_MIN_N wide, 1-CTA kernel for narrow layers
         self.conv_impl = {"simt": _lib.IMPL_SIMT, "tc2": _lib.IMPL_TC2, "tc": _lib.IMPL_TC, "auto": -1}.get(impl, -1)
         self.tc2_min_n = int(os.environ.get("SSP_TC2_MIN_N", "128"))
+        self.use_band = os.environ.get("SSP_BAND", "1") != "0"
         wimpl = os.environ.get("SSP_WGRAD_IMPL", "simt" if impl == "simt" else "tc").lower()
         self.wgrad_impl = _lib.IMPL_SIMT if wimpl == "simt" else _lib.IMPL_TC
         # backward operands: one 16-bit format for dY, W and X (tcgen05 kind::f16 cannot mix fp16 with bf16 -- illegal
@@ -278,10 +279,12 @@ class Engine:
             self._buffers[key] = b
         return b
 
-    def _conv_impl(self, n_out):
+    def _conv_impl(self, n_out, taps=1):
         if self.conv_impl >= 0:
             return self.conv_impl
-        return _lib.IMPL_TC2 if n_out >= self.tc2_min_n else _lib.IMPL_TC
+        if n_out >= self.tc2_min_n:
+            return _lib.IMPL_TC2
+        return _lib.IMPL_BAND if (taps == 9 and self.use_band) else _lib.IMPL_TC
 
     def _gemm(self, kind, L, N, h, w, name, *args, stream=None):
         """launch one GEMM-shaped kernel; optionally bracket it with CUDA events on the launching stream (bench roofline)."""
@@ -297,7 +300,7 @@ class Engine:
 
     def _conv_fwd(self, L, B, N, h, w, xin, a_lo, b_lo, epi, bias, st, s):
         i = L.index
-        self._gemm("fwd", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cout), ptr(xin), a_lo, B.rows[i], xin.shape[1], L.k_cin,
+        self._gemm("fwd", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cout, L.k_taps), ptr(xin), a_lo, B.rows[i], xin.shape[1], L.k_cin,
                    ptr(self.w_hi[i]), b_lo, L.cout, self.w_hi[i].shape[1], _lib.FMT_F16, _lib.FMT_F16,
                    N, h, w, L.k_taps, L.cout, ptr(B.y[i]), B.y[i].shape[1], B.rows[i], epi, bias,
                    ptr(st["ssum"]), ptr(st["ssq"]), s)
@@ -412,7 +415,7 @@ class Engine:
                 ev.record(main)                      # dY of this layer is complete
             if not L.first:                          # data gradient first: it is on the critical path of the next layer
                 wd = self.w_d[i]
-                self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cin), ptr(dy), None, B.rows[i], dy.shape[1], L.cout, ptr(wd), None,
+                self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cin, L.taps), ptr(dy), None, B.rows[i], dy.shape[1], L.cout, ptr(wd), None,
                            L.cin, wd.shape[1], self.grad_fmt, self.grad_fmt, N, h, w, L.taps, L.cin, ptr(B.dx[i]), B.dx[i].shape[1], B.rows[i],
                            _lib.EPI_F32, None, None, None, s)
             if overlap:

@@ -124,3 +124,40 @@ def project_points_batched(points_3D, Rt, internal_calibration):
     out = torch.empty(n, 2, nv, dtype=torch.float32, device=dev)
     call("ssp_project_points", ptr(X), X.shape[0], nv, ptr(T), ptr(K), n, ptr(out), stream_ptr())
     return out
+
+
+# ------------------------------------------------------------------------------------------ batched evaluation tail
+def evaluate_poses_batched(output, target, vertices, points_3D, internal_calibration, num_classes=1, num_keypoints=9,
+                           im_width=640, im_height=480):
+    """GPU-resident version of the per-image evaluation loop of reference valid.py:123-183: per-image decode
+    (arg-max cell of EACH image, not the whole batch), PnP of the ground-truth and the predicted keypoints, reprojection of
+    all mesh vertices, pixel / 3-D / angular / translation errors -- no Python loop over images.
+
+    output (B, 2K+1+C, h, w) CUDA; target (B, >= 2K+1) rows [cls, x0, y0, ..., x8, y8, ...] (first object);
+    vertices (3|4, Nv); points_3D (K, 3); internal_calibration (3, 3).  Returns a dict of CUDA tensors with leading dim B."""
+    dev = output.device
+    K = num_keypoints
+    boxes, best, _ = region_boxes_batched(output, num_classes, K)
+    B = boxes.shape[0]
+    scale = torch.tensor([im_width, im_height], dtype=torch.float32, device=dev)
+    pr2d = boxes[:, :2 * K].reshape(B, K, 2) * scale
+    gt2d = torch.as_tensor(target)[:, 1:1 + 2 * K].to(dev, torch.float32).reshape(B, K, 2) * scale
+    Kc = torch.as_tensor(np.asarray(internal_calibration, dtype=np.float32)).to(dev)
+    P3 = torch.as_tensor(np.asarray(points_3D, dtype=np.float32)).to(dev)
+    R, t = pnp_batched(P3, torch.cat([gt2d, pr2d], 0), Kc)             # 2B problems in one launch
+    R_gt, R_pr, t_gt, t_pr = R[:B], R[B:], t[:B], t[B:]
+    Rt_gt = torch.cat([R_gt, t_gt.unsqueeze(2)], 2)
+    Rt_pr = torch.cat([R_pr, t_pr.unsqueeze(2)], 2)
+    V = torch.as_tensor(np.asarray(vertices, dtype=np.float32)).to(dev)
+    if V.shape[0] == 3:
+        V = torch.cat([V, torch.ones(1, V.shape[1], device=dev)], 0)
+    Kd = Kc.double()
+    proj = project_points_batched(V, torch.cat([Rt_gt, Rt_pr], 0), Kd)  # (2B, 2, Nv)
+    pixel_err = (proj[:B] - proj[B:]).norm(dim=1).mean(dim=1)           # valid.py:169-171 mean 2-D vertex reprojection distance
+    Vd = V.double()
+    tf_gt, tf_pr = Rt_gt @ Vd, Rt_pr @ Vd                               # compute_transformation
+    vertex_dist = (tf_gt - tf_pr).norm(dim=1).mean(dim=1)               # valid.py:176-178
+    tr = torch.einsum("bij,bij->b", R_gt, R_pr)                         # trace(R_gt R_pr^T)
+    angle = torch.rad2deg(torch.arccos(((tr - 1.0) / 2.0).clamp(-1.0, 1.0)))
+    return dict(boxes=boxes, conf=best, corner_err_px=(pr2d - gt2d).norm(dim=2).mean(dim=1), R_gt=R_gt, t_gt=t_gt, R_pr=R_pr, t_pr=t_pr,
+                pixel_err=pixel_err, vertex_dist=vertex_dist, angle_err_deg=angle, trans_err=(t_gt - t_pr).norm(dim=1))

@@ -109,3 +109,41 @@ def test_project_points_matches_numpy():
     for i in range(3):
         ref = utils.compute_projection(X, Rt[i], K)
         np.testing.assert_allclose(got[i], ref, rtol=1e-6, atol=1e-4)
+
+
+def test_evaluate_poses_batched_matches_per_image_loop():
+    """8(f).1: the batched evaluation tail == the reference's per-image loop (valid.py:123-183) built from the
+    reference-API functions (get_region_boxes / pnp / compute_projection / calcAngularDistance)."""
+    gen = torch.Generator().manual_seed(31)
+    B = 6
+    pr = synth.pnp_problems(B, sigma=0.0, seed=12)
+    out = torch.randn(B, 20, 13, 13, generator=gen) * 0.3
+    tgt = torch.zeros(B, 21)
+    for b in range(B):                                   # plant the (noisy) true keypoints in one confident cell per image
+        uvn = pr["uv"][b] / np.array([640.0, 480.0], np.float32) + np.random.default_rng(b).normal(size=(9, 2)).astype(np.float32) * 1e-3
+        cx, cy = int(uvn[0, 0] * 13), int(uvn[0, 1] * 13)
+        cx, cy = min(max(cx, 0), 12), min(max(cy, 0), 12)
+        for k in range(9):
+            vx, vy = uvn[k, 0] * 13 - cx, uvn[k, 1] * 13 - cy
+            if k == 0:
+                vx, vy = np.log(np.clip(vx, 1e-3, 1 - 1e-3) / (1 - np.clip(vx, 1e-3, 1 - 1e-3))), np.log(np.clip(vy, 1e-3, 1 - 1e-3) / (1 - np.clip(vy, 1e-3, 1 - 1e-3)))
+            out[b, 2 * k, cy, cx] = float(vx); out[b, 2 * k + 1, cy, cx] = float(vy)
+        out[b, 18, cy, cx] = 6.0
+        tgt[b, 1:19] = torch.from_numpy((pr["uv"][b] / np.array([640.0, 480.0], np.float32)).reshape(-1))
+    rng = np.random.default_rng(3)
+    verts = np.concatenate([rng.uniform(-0.04, 0.04, size=(3, 500)), np.ones((1, 500))]).astype(np.float64)
+    Kc = synth.intrinsics()
+    res = utils.evaluate_poses_batched(out.cuda(), tgt, verts, pr["P3"], Kc)
+    for b in range(B):
+        box = utils.get_region_boxes(out[b:b + 1].cuda(), 1, 9)
+        c_pr = np.array([float(v) for v in box[:18]], np.float32).reshape(9, 2) * np.array([640, 480], np.float32)
+        c_gt = tgt[b, 1:19].numpy().reshape(9, 2) * np.array([640, 480], np.float32)
+        R_gt, t_gt = utils.pnp(pr["P3"], c_gt, Kc.astype(np.float32))
+        R_pr, t_pr = utils.pnp(pr["P3"], c_pr, Kc.astype(np.float32))
+        Rt_gt, Rt_pr = np.concatenate((R_gt, t_gt), 1), np.concatenate((R_pr, t_pr), 1)
+        p_gt, p_pr = utils.compute_projection(verts, Rt_gt, Kc), utils.compute_projection(verts, Rt_pr, Kc)
+        assert float(res["pixel_err"][b]) == pytest.approx(np.mean(np.linalg.norm(p_gt - p_pr, axis=0)), rel=1e-3, abs=1e-3)
+        v_gt, v_pr = utils.compute_transformation(verts, Rt_gt), utils.compute_transformation(verts, Rt_pr)
+        assert float(res["vertex_dist"][b]) == pytest.approx(np.mean(np.linalg.norm(v_gt - v_pr, axis=0)), rel=1e-3, abs=1e-6)
+        assert float(res["angle_err_deg"][b]) == pytest.approx(utils.calcAngularDistance(R_gt, R_pr), abs=1e-3)
+        assert float(res["trans_err"][b]) == pytest.approx(np.linalg.norm(t_gt - t_pr), rel=1e-3, abs=1e-6)

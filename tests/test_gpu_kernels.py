@@ -69,6 +69,7 @@ def _pack_w(w, split=True, fmt=_lib.FMT_F16, dgrad=False):
 CONV_CASES = [
     # N, H, W, cin, cout, k, bias
     (2, 12, 12, 64, 64, 3, False),
+    (2, 40, 24, 32, 64, 3, False),           # block-2 shape class: band loads + resident weights
     (1, 13, 13, 128, 256, 3, False),
     (3, 5, 7, 64, 32, 3, False),
     (2, 26, 26, 256, 128, 1, False),
@@ -78,7 +79,7 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("impl", [_lib.IMPL_SIMT, _lib.IMPL_TC, _lib.IMPL_TC2])
+@pytest.mark.parametrize("impl", [_lib.IMPL_SIMT, _lib.IMPL_TC, _lib.IMPL_TC2, _lib.IMPL_BAND])
 def test_conv_gemm_matches_torch(case, impl):
     N, H, W, cin, cout, k, use_bias = case
     g = torch.Generator().manual_seed(hash(case) % 1000)
@@ -116,7 +117,7 @@ def test_conv_gemm_single_term_bf16_dgrad_layout():
     w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
     dyq = dy.bfloat16().float(); wq = w.bfloat16().float()
     ref = F.conv_transpose2d(dyq.double(), wq.double(), padding=1).float()
-    for impl in (_lib.IMPL_SIMT, _lib.IMPL_TC, _lib.IMPL_TC2):
+    for impl in (_lib.IMPL_SIMT, _lib.IMPL_TC, _lib.IMPL_TC2, _lib.IMPL_BAND):
         dyh, _, rows = flat_from_nchw(dy.to(DEV), fmt=_lib.FMT_BF16, split=False)
         _, _, wd = _pack_w(w.to(DEV), fmt=_lib.FMT_BF16, dgrad=True)
         dx = torch.zeros(rows, cin, device=DEV)
