@@ -18,7 +18,7 @@ int conv_gemm_tc(const void*, const void*, long long, int, int, const void*, con
 int conv_gemm_tc2(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
                   float*, int, long long, int, const float*, double*, double*, cudaStream_t);
 int conv_gemm_band(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
-                   float*, int, long long, int, const float*, double*, double*, int, cudaStream_t);
+                   float*, int, long long, int, const float*, double*, double*, cudaStream_t);
 int conv_gemm_simt(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
                    float*, int, long long, int, const float*, double*, double*, cudaStream_t);
 int conv0_direct(const float*, const float*, const float*, float*, int, double*, double*, int, int, int, cudaStream_t);
@@ -70,9 +70,7 @@ int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo, long long a_rows
   if (impl == SSP_IMPL_SIMT)
     return conv_gemm_simt(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
   if (impl == SSP_IMPL_BAND) {
-    static int baseoff = -1;
-    if (baseoff < 0) { const char* e = getenv("SSP_BAND_BASEOFF"); baseoff = (e && e[0] == '1') ? 1 : 0; }
-    const int rc = conv_gemm_band(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, baseoff, ST(s));
+    const int rc = conv_gemm_band(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
     if (rc != 1) return rc;          // 1 = layer not eligible (weights do not fit): per-tap kernel below
   }
   if (impl == SSP_IMPL_TC2)

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) conv_band_kernel(const __grid_co
 int conv_gemm_band(const void* a_hi, const void* a_lo, long long a_rows, int a_ld, int cin,
                    const void* b_hi, const void* b_lo, int b_rows, int b_ld, int a_fmt, int b_fmt,
                    int N, int H, int W, int taps, int cout, float* out, int out_ld, long long out_rows,
-                   int epi, const float* bias, double* stat_sum, double* stat_sq, int baseoff, cudaStream_t stream) {
+                   int epi, const float* bias, double* stat_sum, double* stat_sq, cudaStream_t stream) {
   if (taps != 9 || cout > 256) return 1;
   if (!a_hi || !b_hi || !out || (a_ld % 8) || (b_ld % 8) || (out_ld % 4)) return fail_msg(SSP_ERR_ARG, "conv_gemm_band: bad argument");
   ConvBandParams p;
