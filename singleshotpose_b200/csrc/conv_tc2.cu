@@ -291,15 +291,8 @@ int conv_gemm_tc2(const void* a_hi, const void* a_lo, long long a_rows, int a_ld
   if (bn > 256) bn = 256;
   if (bn > 128 && bn < 256) bn = 256;
   if (bn > 64 && bn < 128) bn = 128;
-  if (bn == 256 && g_num_sms2 >= 2) {
-    // wave quantisation: with few 256-row pair tiles a narrower N tile can fill the last wave better
-    // (e.g. N = 512 on the 13x13 maps: 98 tiles on 74 pairs = 2 waves of 256 vs 3 waves of 128)
-    const long long mt = (g.m_rows() + 255) / 256;
-    const int pairs_hw = g_num_sms2 / 2;
-    const long long w256 = (mt * ((cout + 255) / 256) + pairs_hw - 1) / pairs_hw * 256;
-    const long long w128 = (mt * ((cout + 127) / 128) + pairs_hw - 1) / pairs_hw * 128;
-    if (w128 * 110 < w256 * 100) bn = 128;      // 10 % penalty for the lower arithmetic intensity of the narrow tile
-  }
+  // (a narrower N tile would fill the last wave better on the 13x13 maps, but halves the arithmetic intensity per
+  //  activation byte: measured 1.4x slower, so the tile stays 256 wide wherever the layer allows it)
   p.bn = bn;
   p.b_bytes = (bn / 2) * 128;       // per CTA: half of the weight tile
   p.m_rows = g.m_rows();
