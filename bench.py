@@ -293,10 +293,14 @@ def main():
     ms_e = float(tmax.item())
     e2e = gb * args.steps / (ms_e * 1e-3)
 
+    if world > 1:
+        # every rank is done with collectives here.  The captured graph holds NCCL kernels; tearing the process group
+        # down underneath it can dead-lock, so the ranks synchronise once more and leave without the collective shutdown.
+        dist.barrier()
+        torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        sys.stdout.flush()
+        os._exit(0)
     # ---------------- roofline of the dominant kernel from the per-launch events ----------------
     pk = peaks()
     agg = {}
@@ -373,8 +377,9 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "pnp": pnp,
     }
     print(json.dumps(out))
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        os._exit(0)
 
 
 def np_zeros8():
