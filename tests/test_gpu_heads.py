@@ -147,3 +147,34 @@ def test_evaluate_poses_batched_matches_per_image_loop():
         assert float(res["vertex_dist"][b]) == pytest.approx(np.mean(np.linalg.norm(v_gt - v_pr, axis=0)), rel=1e-3, abs=1e-6)
         assert float(res["angle_err_deg"][b]) == pytest.approx(utils.calcAngularDistance(R_gt, R_pr), abs=1e-3)
         assert float(res["trans_err"][b]) == pytest.approx(np.linalg.norm(t_gt - t_pr), rel=1e-3, abs=1e-6)
+
+
+def test_region_loss_image_without_ground_truth():
+    """Edge case: an image whose label row is empty (x0 == 0).  The reference raises IndexError there
+    (region_loss.py:40); here it contributes only the no-object confidence term."""
+    gen = torch.Generator().manual_seed(41)
+    out = torch.randn(3, 20, 13, 13, generator=gen)
+    tgt = synth.targets(3, seed=42)
+    tgt[1] = 0
+    crit = RegionLoss(); crit.verbose = False
+    od = out.cuda().requires_grad_(True)
+    loss = crit(od, tgt, 20)
+    loss.backward()
+    st = crit.stats()
+    assert st["nGT"] == 2 and torch.isfinite(loss)
+    o2 = torch.cat([out[0:1], out[2:3]]).requires_grad_(True)
+    l_ref, _ = RL.region_loss_ref(o2, torch.cat([tgt[0:1], tgt[2:3]]), 20)
+    conf1 = torch.sigmoid(out[1, 18])
+    expect = float(l_ref) + 0.5 * float((conf1 ** 2).sum())          # noobject_scale 1, tconf 0
+    assert float(loss) == pytest.approx(expect, rel=1e-4)
+    assert float(od.grad[1, :18].abs().max()) == 0.0
+
+
+def test_pnp_minimum_points_and_argument_errors():
+    from singleshotpose_b200._lib import SspError
+    pr = synth.pnp_problems(3, sigma=0.0, seed=8)
+    R, t = utils.pnp_batched(pr["P3"][:6], pr["uv"][:, :6], pr["K"])           # 6 points: the DLT minimum
+    for i in range(3):
+        assert _ang(R[i].cpu().numpy(), pr["R"][i]) < 1e-2
+    with pytest.raises(SspError):
+        utils.pnp_batched(pr["P3"][:5], pr["uv"][:, :5], pr["K"])              # under-determined: rejected like cv2's CV_Assert
