@@ -313,15 +313,16 @@ def main():
     conv_flops, conv_t, conv_n = cf[0] + cd[0], cf[1] + cd[1], cf[2] + cd[2]
     achieved = conv_flops / conv_t / 1e12 if conv_t else 0.0
     executed = (3.0 * cf[0] + cd[0]) / conv_t / 1e12 if conv_t else 0.0     # forward launches issue 3 MMAs per algorithmic MAC
-    traffic = None
+    traffic, traffic_detail = None, None
     tp = os.path.join(ROOT, "profiles", "conv_traffic.json")                 # per-launch DRAM bytes from the committed ncu --set full capture
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp))
+            traffic_detail = json.load(open(tp))
+            traffic = traffic_detail["dram_bytes_read"] + traffic_detail["dram_bytes_write"]
         except Exception:
-            traffic = None
+            traffic, traffic_detail = None, None
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (forward + data-gradient launches)", "achieved": achieved, "peak": pk["tflops"],
-                "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic, "peak_source": pk["src"],
+                "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": pk["src"],
                 "executed_tflops": executed, "frac_executed": executed / pk["tflops"],
                 "launches_per_step": conv_n // max(args.steps, 1), "share_of_step": conv_t / (ms_eager * 1e-3) if ms_eager else None,
                 "measured_in": "separate eager pass of the same %d steps (%.2f ms/step) with an event pair around every GEMM launch" % (args.steps, ms_eager / args.steps),
@@ -363,6 +364,33 @@ def main():
         except Exception as ex:                                  # cv2 missing: baseline omitted, GPU number stands
             pnp["cpu_cv2_poses_per_s"] = None
             pnp["cpu_sample"] = "unavailable: %s" % type(ex).__name__
+    # ---------------- inference path of valid.py (BASELINE.json configs[0]): eval forward + decode + PnP ----------------
+    infer = None
+    if world == 1 and not args.no_pnp:
+        model.eval()
+        P3i = torch.from_numpy(synth.box_points()).to(dev); Ki = torch.from_numpy(synth.intrinsics(np_f32())).to(dev)
+        scale = torch.tensor([640.0, 480.0], device=dev)
+
+        def infer_step(xb):
+            with torch.no_grad():
+                o = model(xb)
+                boxes, _, _ = utils.region_boxes_batched(o, 1, 9)
+                return utils.pnp_batched(P3i, boxes[:, :18].reshape(-1, 9, 2) * scale, Ki)
+        infer = {}
+        for bsz in (1, 64):
+            xb = x_dev[:bsz]
+            for _ in range(3):
+                infer_step(xb)
+            torch.cuda.synchronize()
+            e0.record()
+            reps = 20 if bsz == 1 else 5
+            for _ in range(reps):
+                infer_step(xb)
+            e1.record(); torch.cuda.synchronize()
+            msi = e0.elapsed_time(e1) / reps
+            infer["batch%d" % bsz] = {"ms": msi, "images_per_s": bsz / (msi * 1e-3)}
+        infer["what"] = "eval-mode forward (running-stat BN) + per-image decode + PnP, eager launches, inputs resident in HBM"
+        model.train()
     out = {
         "metric": "images/sec fwd+bwd+SGD (416x416, yolo-pose.cfg)", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -374,12 +402,17 @@ def main():
         "gpu_launches": launches, "clocks": clocks,
         "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e / args.steps,
                 "h2d_bytes_per_step": x_host.numel() * 4 + t_host.numel() * 4, "d2h_bytes_per_step": 4},
-        "roofline": roofline, "cpu_baseline": cpu, "pnp": pnp,
+        "roofline": roofline, "cpu_baseline": cpu, "pnp": pnp, "inference": infer,
     }
     print(json.dumps(out))
     sys.stdout.flush()
     if world > 1:
         os._exit(0)
+
+
+def np_f32():
+    import numpy as np
+    return np.float32
 
 
 def np_zeros8():
