@@ -34,14 +34,16 @@ __global__ void __launch_bounds__(kPix, 2) conv0_direct_kernel(const float* __re
       const unsigned up = (unsigned)pix, tq = up / (unsigned)W;       // 32-bit index math (64-bit div/mod is ~10x the cost)
       const unsigned w = up - tq * (unsigned)W, n = tq / (unsigned)H, h = tq - n * (unsigned)H;
       orow = g.row((int)n, (int)h, (int)w);
-      const float* xb = x + (long long)n * 3 * H * W;
-#pragma unroll
+      const int HW = H * W;
+      const float* px = x + (long long)n * 3 * HW + (int)(h * W + w);     // this pixel, channel 0: one 64-bit address per pixel,
+#pragma unroll                                                            // the 27 taps are small 32-bit offsets from it
       for (int tap = 0; tap < 9; tap++) {
         const int hh = (int)h + tap / 3 - 1, ww = (int)w + tap % 3 - 1;
         const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
+        const int off = (tap / 3 - 1) * W + (tap % 3 - 1);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          const float v = in ? __ldg(xb + ((long long)c * H + hh) * W + ww) : 0.f;
+          const float v = in ? __ldg(px + (c * HW + off)) : 0.f;
           const float4* wr = reinterpret_cast<const float4*>(&sw[tap * 3 + c][0]);
 #pragma unroll
           for (int q = 0; q < kC0 / 4; q++) {

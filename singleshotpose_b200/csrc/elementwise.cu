@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(256) pack_input_im2col_kernel(const float* __r
   const int h = (int)((pix / W) % H);
   const int n = (int)(pix / ((long long)W * H));
   uint32_t ph[16], pl[16];
+  const int HW = H * W;
+  const float* px = x + (long long)n * 3 * HW + (h * W + w);     // one 64-bit address per pixel; taps are 32-bit offsets
 #pragma unroll
   for (int k2 = 0; k2 < 16; k2++) {
     uint16_t a[2], b[2];
@@ -29,7 +31,7 @@ __global__ void __launch_bounds__(256) pack_input_im2col_kernel(const float* __r
       if (k < 27) {
         const int c = k % 3, tap = k / 3;
         const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + (((long long)n * 3 + c) * H + hh) * W + ww);
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(px + (c * HW + (tap / 3 - 1) * W + (tap % 3 - 1)));
       }
       split_f16(v, a[e], b[e]);
     }

@@ -124,6 +124,13 @@ def test_other_resolution_and_weights_roundtrip(cfg_path, tmp_path):
     with torch.no_grad():
         o = m(synth.images(1, 352, 480, seed=5).cuda())            # multi-resolution training shapes (dataset.py:66-90)
     assert o.shape == (1, 20, 11, 15)
+    with torch.no_grad():
+        o672 = m(synth.images(1, m.test_height, m.test_width, seed=6).cuda())   # valid.py evaluates at test_width x test_height = 672
+    assert o672.shape == (1, 20, 21, 21) and torch.isfinite(o672).all()
+    dp = torch.nn.DataParallel(m, device_ids=[0])                           # train_multi.py:387 wraps the model like this
+    with torch.no_grad():
+        o_dp = dp(synth.images(1, 352, 480, seed=5).cuda())
+    assert torch.equal(o_dp, o) and dp.module.num_keypoints == 9
     f = str(tmp_path / "m.weights")
     m.seen = 1234
     m.save_weights(f)
