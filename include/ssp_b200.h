@@ -61,6 +61,13 @@ int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo_or_null, long lon
                   const void* b_hi, const void* b_lo_or_null, int b_rows, int b_ld, int a_fmt, int b_fmt,
                   int N, int H, int W, int taps, int cout, float* out, int out_ld, long long out_rows, int epi,
                   const float* bias, double* stat_sum, double* stat_sq, void* stream);
+/* ---- inference: nn.Conv2d + nn.BatchNorm2d(eval) + nn.LeakyReLU as ONE kernel (darknet.py:154-164 under model.eval()):
+ *      z = leaky(conv * scale[c] + shift[c]) is written by the GEMM epilogue straight into the consumer's fp16 hi/lo operand
+ *      planes (rows [row][d_ld], channel offset d_c0); scale/shift from ssp_bn_finalize(train=0).  fp16 hi/lo operands. ---- */
+int ssp_conv_gemm_bnact(int impl, const void* a_hi, const void* a_lo, long long a_rows, int a_ld, int cin,
+                        const void* b_hi, const void* b_lo, int b_rows, int b_ld, int N, int H, int W, int taps, int cout,
+                        const float* scale, const float* shift, float slope, void* d_hi, void* d_lo, int d_ld, int d_c0,
+                        void* stream);
 /* ---- first layer nn.Conv2d(3, 32, 3, 1, 1) (darknet.py:156, block 0): direct fp32 convolution of the NCHW image with the
  *      fp32 master weights [32][3][3][3] (k = (kh*3+kw)*3 + ci), output rows [row(n,h,w)][y_ld], optional fp64 BN statistics ---- */
 int ssp_conv0_direct(const float* x_nchw, const float* w, const float* bias_or_null, float* y, int y_ld,

@@ -14,9 +14,9 @@ int fail_cuda(cudaError_t e, const char* file, int line) {
 int fail_msg(int code, const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); return code; }
 
 int conv_gemm_tc(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
-                 float*, int, long long, int, const float*, double*, double*, cudaStream_t);
+                 float*, int, long long, int, const float*, double*, double*, cudaStream_t, const FusedAct*);
 int conv_gemm_tc2(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
-                  float*, int, long long, int, const float*, double*, double*, cudaStream_t);
+                  float*, int, long long, int, const float*, double*, double*, cudaStream_t, const FusedAct*);
 int conv_gemm_band(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
                    float*, int, long long, int, const float*, double*, double*, cudaStream_t);
 int conv_gemm_simt(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
@@ -74,11 +74,23 @@ int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo, long long a_rows
     if (rc != 1) return rc;          // 1 = layer not eligible (weights do not fit): per-tap kernel below
   }
   if (impl == SSP_IMPL_TC2)
-    return conv_gemm_tc2(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
-  return conv_gemm_tc(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
+    return conv_gemm_tc2(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s), nullptr);
+  return conv_gemm_tc(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s), nullptr);
 }
 int ssp_conv0_direct(const float* x, const float* w, const float* bias, float* y, int y_ld, double* ssum, double* ssq, int N, int H, int W, void* s) {
   return conv0_direct(x, w, bias, y, y_ld, ssum, ssq, N, H, W, ST(s));
+}
+int ssp_conv_gemm_bnact(int impl, const void* a_hi, const void* a_lo, long long a_rows, int a_ld, int cin, const void* b_hi, const void* b_lo,
+                        int b_rows, int b_ld, int N, int H, int W, int taps, int cout, const float* scale, const float* shift, float slope,
+                        void* d_hi, void* d_lo, int d_ld, int d_c0, void* s) {
+  FusedAct fa{scale, shift, slope, (uint16_t*)d_hi, (uint16_t*)d_lo, d_ld, d_c0};
+  if (impl == SSP_IMPL_TC2)
+    return conv_gemm_tc2(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, SSP_FMT_F16, SSP_FMT_F16, N, H, W, taps, cout, nullptr, 0, 0, EPI_BNACT,
+                         nullptr, nullptr, nullptr, ST(s), &fa);
+  if (impl == SSP_IMPL_TC || impl == SSP_IMPL_BAND)
+    return conv_gemm_tc(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, SSP_FMT_F16, SSP_FMT_F16, N, H, W, taps, cout, nullptr, 0, 0, EPI_BNACT,
+                        nullptr, nullptr, nullptr, ST(s), &fa);
+  return fail_msg(SSP_ERR_ARG, "ssp_conv_gemm_bnact: tensor-core implementations only");
 }
 int ssp_wgrad_gemm(int impl, const void* dy, long long dy_rows, int dy_ld, int cout, int dy_fmt, const void* x, long long x_rows, int x_ld,
                    int cin, int x_fmt, int N, int H, int W, int taps, float* dw, int dw_ld, int cin_store, float scale, void* s) {

@@ -40,6 +40,7 @@ struct ConvTcParams {
   double* stat_sum;
   double* stat_sq;
   int epi;
+  FusedAct fa;            // EPI_BNACT only
 };
 
 static constexpr int kABytes = 128 * 128;     // 128 rows x 64 x 2 B
@@ -47,6 +48,7 @@ static constexpr int kMaxStages = 8;
 static constexpr int kAccCols = 1024;         // per-CTA statistics accumulators (channels)
 static constexpr int kThreads = 256;
 
+template <bool FUSED>   // FUSED: the inference epilogue (EPI_BNACT) -- a separate instantiation keeps the training kernel's code unchanged
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16-B aligned: round up to 1024 (swizzle-128B atoms)
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.bn);
-      float* orow = p.out + m * p.out_ld;
+      float* orow = p.out ? p.out + m * p.out_ld : nullptr;
       const bool can_store = m < p.store_rows;
       for (int ch = 0; ch < p.bn / 32; ch++) {
         uint32_t r[32];
@@ -174,6 +176,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+        if constexpr (FUSED) {
+          // folded BatchNorm (running statistics) + LeakyReLU in the epilogue; only valid rows are written so that the
+          // consumer's pad rows stay zero; the fp32 Y tensor is never materialised in this mode
+          if (valid && c0 + 32 <= p.cout) {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              uint16_t h0, l0, h1, l1;
+              float z0 = fmaf(v[j], __ldg(p.fa.scale + c0 + j), __ldg(p.fa.shift + c0 + j));
+              float z1 = fmaf(v[j + 1], __ldg(p.fa.scale + c0 + j + 1), __ldg(p.fa.shift + c0 + j + 1));
+              z0 = z0 > 0.f ? z0 : z0 * p.fa.slope; z1 = z1 > 0.f ? z1 : z1 * p.fa.slope;
+              split_f16(z0, h0, l0); split_f16(z1, h1, l1);
+              ph[j >> 1] = h0 | ((uint32_t)h1 << 16); pl[j >> 1] = l0 | ((uint32_t)l1 << 16);
+            }
+            uint4* dh = reinterpret_cast<uint4*>(p.fa.d_hi + m * p.fa.d_ld + p.fa.d_c0 + c0);
+            uint4* dl = reinterpret_cast<uint4*>(p.fa.d_lo + m * p.fa.d_ld + p.fa.d_c0 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              dh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+              dl[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+            }
+          }
+          continue;
+        }
         if (p.epi == EPI_BIAS) {
 #pragma unroll
           for (int j = 0; j < 32; j++) if (c0 + j < p.cout) v[j] += __ldg(p.bias + c0 + j);
@@ -222,12 +248,17 @@ static int g_num_sms = 0;
 int conv_gemm_tc(const void* a_hi, const void* a_lo, long long a_rows, int a_ld, int cin,
                  const void* b_hi, const void* b_lo, int b_rows, int b_ld, int a_fmt, int b_fmt,
                  int N, int H, int W, int taps, int cout, float* out, int out_ld, long long out_rows,
-                 int epi, const float* bias, double* stat_sum, double* stat_sq, cudaStream_t stream) {
-  if (!a_hi || !b_hi || !out || (taps != 1 && taps != 9) || cin <= 0 || cout <= 0) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc: bad argument");
+                 int epi, const float* bias, double* stat_sum, double* stat_sq, cudaStream_t stream, const FusedAct* fa) {
+  if (fa) {
+    if (!fa->scale || !fa->shift || !fa->d_hi || !fa->d_lo || (cout % 32) || (fa->d_ld % 8) || (fa->d_c0 % 8))
+      return fail_msg(SSP_ERR_ARG, "conv_gemm_tc: fused BN+activation epilogue needs cout % 32 == 0 and 16-B aligned destination rows");
+    epi = EPI_BNACT;
+  }
+  if (!a_hi || !b_hi || (!out && !fa) || (taps != 1 && taps != 9) || cin <= 0 || cout <= 0) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc: bad argument");
   if ((a_ld % 8) || (b_ld % 8)) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc: leading dimensions must be multiples of 8 elements (16 B)");
   if (epi == EPI_STATS && (cout > kAccCols || !stat_sum || !stat_sq)) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc: statistics need cout <= 1024 and buffers");
   if (epi == EPI_BIAS && !bias) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc: bias missing");
-  if ((out_ld % 4) || ((uintptr_t)out % 16)) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc: output must be 16-B aligned with ld % 4 == 0");
+  if (!fa && ((out_ld % 4) || ((uintptr_t)out % 16))) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc: output must be 16-B aligned with ld % 4 == 0");
   if (!g_num_sms) {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -259,6 +290,7 @@ int conv_gemm_tc(const void* a_hi, const void* a_lo, long long a_rows, int a_ld,
   if (stages < 2) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc: tile does not fit shared memory");
   p.stages = stages;
   p.out = out; p.out_ld = out_ld; p.bias = bias; p.stat_sum = stat_sum; p.stat_sq = stat_sq; p.epi = epi;
+  if (fa) p.fa = *fa; else p.fa = FusedAct{nullptr, nullptr, 1.f, nullptr, nullptr, 0, 0};
   int rc = 0;
   rc |= tmap_2d_16bit(&p.tmA[0], a_hi, (uint64_t)cin, (uint64_t)a_rows, (uint64_t)a_ld, 64, 128, a_fmt == FMT_BF16);
   rc |= tmap_2d_16bit(&p.tmB[0], b_hi, (uint64_t)taps * cin, (uint64_t)b_rows, (uint64_t)b_ld, 64, bn, b_fmt == FMT_BF16);
@@ -270,13 +302,15 @@ int conv_gemm_tc(const void* a_hi, const void* a_lo, long long a_rows, int a_ld,
   const int smem_bytes = stages * p.stage_bytes + fixed;
   static int configured = 0;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, __FILE__, __LINE__);
     configured = 1;
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  conv_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+  if (fa) conv_tc_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(p);
+  else conv_tc_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(p);
   SSP_CHECK_LAUNCH();
   return SSP_OK;
 }

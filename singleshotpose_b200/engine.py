@@ -160,6 +160,7 @@ class Engine:
         self.conv_impl = {"simt": _lib.IMPL_SIMT, "tc2": _lib.IMPL_TC2, "tc": _lib.IMPL_TC, "auto": -1}.get(impl, -1)
         self.tc2_min_n = int(os.environ.get("SSP_TC2_MIN_N", "128"))
         self.use_band = os.environ.get("SSP_BAND", "1") != "0"
+        self.fuse_eval = os.environ.get("SSP_FUSE_EVAL", "1") != "0"
         wimpl = os.environ.get("SSP_WGRAD_IMPL", "simt" if impl == "simt" else "tc").lower()
         self.wgrad_impl = _lib.IMPL_SIMT if wimpl == "simt" else _lib.IMPL_TC
         # backward operands: one 16-bit format for dY, W and X (tcgen05 kind::f16 cannot mix fp16 with bf16 -- illegal
@@ -335,6 +336,19 @@ class Engine:
                 bias = None
             else:
                 epi, bias = _lib.EPI_BIAS, ptr(conv.bias.data)
+            fuse = (L.bn and not train_bn and not keep_for_backward and self.fuse_eval and not L.first
+                    and self.conv_impl != _lib.IMPL_SIMT and len(L.dests) == 1 and L.dests[0][2] == _lib.ROUTE_DIRECT and L.cout % 32 == 0)
+            if fuse:
+                # inference: BN(running stats) + LeakyReLU folded into the GEMM epilogue, which writes the consumer's operand
+                # planes directly -- no fp32 Y, no bn_apply pass (reference: conv, bn, leaky as three modules, darknet.py:154-164)
+                call("ssp_bn_finalize", None, None, 1.0, ptr(bn.weight.data), ptr(bn.bias.data), ptr(bn.running_mean), ptr(bn.running_var),
+                     0.1, float(bn.eps), 0, ptr(st["mean"]), ptr(st["invstd"]), ptr(st["scale"]), ptr(st["shift"]), L.cout, s)
+                ci, c0, _k = L.dests[0]
+                self._gemm("fwd", L, N, h, w, "ssp_conv_gemm_bnact", self._conv_impl(L.cout, L.k_taps), ptr(xin), a_lo, B.rows[i], xin.shape[1],
+                           L.k_cin, ptr(self.w_hi[i]), b_lo, L.cout, self.w_hi[i].shape[1], N, h, w, L.k_taps, L.cout,
+                           ptr(st["scale"]), ptr(st["shift"]), L.slope, ptr(B.x_hi[ci]), ptr(B.x_lo[ci]), B.x_hi[ci].shape[1], c0, s)
+                self.launches += 1          # bn_finalize (the GEMM is counted by _gemm)
+                continue
             if L.first and direct0 and L.bn:       # exact fp32 direct convolution of the raw image (HBM-bound layer)
                 off, n, _gv = self._slices[id(conv.weight)]
                 call("ssp_conv0_direct", ptr(x), ptr(self.flat_params[off:off + n]), None, ptr(B.y[i]), B.y[i].shape[1],

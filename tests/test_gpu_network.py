@@ -94,6 +94,28 @@ def test_eval_forward_matches_oracle_and_golden(pair, golden_dir):
     assert _rel(o1.cpu(), o_ref[:1]) < 1e-3
 
 
+def test_eval_fused_epilogue_matches_unfused(cfg_path):
+    """inference folds BN(running stats)+LeakyReLU into the GEMM epilogue (ssp_conv_gemm_bnact); the unfused three-kernel chain
+    (conv -> bn_finalize -> bn_apply) computes the same fmaf/leaky/split per element, so logits agree to rounding."""
+    torch.manual_seed(5)
+    m = Darknet(cfg_path).cuda().train()
+    with torch.no_grad():
+        for s in (0, 10, 11):                                 # non-trivial running statistics
+            m(synth.images(2, seed=s).cuda())
+    m.eval()
+    eng = m._engine
+    for n, hw in ((1, (416, 416)), (3, (352, 480))):
+        x = synth.images(n, hw[0], hw[1], seed=7).cuda()
+        with torch.no_grad():
+            eng.fuse_eval = True
+            l0 = eng.launches; o_f = m(x); n_f = eng.launches - l0
+            eng.fuse_eval = False
+            l0 = eng.launches; o_u = m(x); n_u = eng.launches - l0
+            eng.fuse_eval = True
+        assert n_f < n_u                                      # the fused path really ran (one launch fewer per fused layer)
+        assert torch.isfinite(o_f).all() and _rel(o_f, o_u) < 2e-5
+
+
 def test_sgd_step_matches_torch_optimizer(cfg_path):
     """FlatSGD (one fused kernel) and torch.optim.SGD on the permuted parameter views give the same update."""
     torch.manual_seed(1)
