@@ -49,3 +49,59 @@ class FlatSGD:
              float(g["lr"]), float(g["momentum"]), float(g["weight_decay"]), float(grad_scale), stream_ptr())
         eng.launches += 1
         eng._weights_version = None            # the next forward re-packs the fp16 operand copies of the weights
+
+    # ------------------------------------------------------------------ checkpointing (absent in the reference,
+    # which only saves model weights -- train.py:409).  The layout is torch.optim.SGD's own state_dict, so a checkpoint moves
+    # freely between FlatSGD and the `optim.SGD(model.parameters(), ...)` of train.py:388.
+    def _momentum_views(self):
+        """per-parameter views of the flat momentum buffer, shaped like the parameters (conv weights: OIHW view of OHWI storage)"""
+        eng = self.model._engine
+        out = []
+        for p in self.model.parameters():
+            off, n, _g = eng._slices[id(p)]
+            v = self._v[off:off + n]
+            if p.dim() == 4:
+                co, ci, kh, kw = p.shape
+                out.append(v.view(co, kh, kw, ci).permute(0, 3, 1, 2))
+            else:
+                out.append(v.view(p.shape))
+        return out
+
+    def state_dict(self):
+        g = self.param_groups[0]
+        n = len(list(self.model.parameters()))
+        group = dict(lr=g["lr"], momentum=g["momentum"], dampening=0, weight_decay=g["weight_decay"], nesterov=False,
+                     maximize=False, foreach=None, differentiable=False, fused=None, params=list(range(n)))
+        state = {}
+        if self._v is not None:
+            state = {i: {"momentum_buffer": v.detach().clone().contiguous()} for i, v in enumerate(self._momentum_views())}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        eng = self.model._engine
+        if eng.flat_params is None:
+            raise RuntimeError("FlatSGD.load_state_dict() needs materialised parameters: move the model to its device and run one "
+                               "forward pass (or call model._engine.materialize(device)) first")
+        groups = sd["param_groups"]
+        if len(groups) != 1:
+            raise ValueError("FlatSGD has one parameter group (train.py:388 passes model.parameters()), got %d" % len(groups))
+        g = groups[0]
+        if g.get("dampening", 0) != 0 or g.get("nesterov", False):
+            raise ValueError("FlatSGD implements optim.SGD(dampening=0, nesterov=False) only (train.py:388)")
+        params = list(self.model.parameters())
+        if len(g["params"]) != len(params):
+            raise ValueError("checkpoint has %d parameters, the model %d" % (len(g["params"]), len(params)))
+        self.param_groups[0].update(lr=g["lr"], momentum=g["momentum"], weight_decay=g["weight_decay"])
+        state = sd.get("state", {})
+        if not state:
+            self._v = None
+            return
+        self._v = torch.zeros_like(eng.flat_params)
+        for i, (p, view) in enumerate(zip(params, self._momentum_views())):
+            ent = state.get(i, state.get(str(i)))
+            if ent is None or ent.get("momentum_buffer") is None:
+                continue                      # optim.SGD creates buffers lazily; a missing one is zero
+            buf = ent["momentum_buffer"]
+            if tuple(buf.shape) != tuple(p.shape):
+                raise ValueError("momentum_buffer %d has shape %s, parameter %s" % (i, tuple(buf.shape), tuple(p.shape)))
+            view.copy_(buf.to(device=view.device, dtype=torch.float32))

@@ -153,3 +153,65 @@ def test_bench_reference_arm_other_ranks_exit():
     r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_optimizer_state_checkpoint_interchanges_with_torch_sgd(cfg_path):
+    """FlatSGD.state_dict()/load_state_dict() speak torch.optim.SGD's format: momentum buffers are stored flat in
+    the kernel's OHWI layout but exchanged as OIHW tensors, so a checkpoint moves between FlatSGD and train.py:388's optimiser."""
+    import torch
+    from singleshotpose_b200.darknet import Darknet
+    from singleshotpose_b200.optim import FlatSGD
+    torch.manual_seed(0)
+    m = Darknet(cfg_path)
+    m._engine.materialize(torch.device("cpu"))                       # flat buffers + views; no kernel involved
+    params = list(m.parameters())
+    ref = torch.optim.SGD(params, lr=1e-3, momentum=0.9, dampening=0, weight_decay=0.032)
+    gen = torch.Generator().manual_seed(1)
+    for p in params[:6] + params[-2:]:                               # optim.SGD keeps buffers only for parameters it stepped
+        ref.state[p]["momentum_buffer"] = torch.randn(p.shape, generator=gen)
+    sd = ref.state_dict()
+    opt = FlatSGD(m, lr=5.0, momentum=0.0, weight_decay=0.0)
+    opt.load_state_dict(sd)
+    assert opt.param_groups[0] == dict(lr=1e-3, momentum=0.9, weight_decay=0.032)
+    w0 = params[0]
+    off, n, _ = m._engine._slices[id(w0)]
+    want = sd["state"][0]["momentum_buffer"].permute(0, 2, 3, 1).reshape(-1)          # flat storage is [co][kh][kw][ci]
+    assert torch.equal(opt._v[off:off + n], want)
+    out = opt.state_dict()
+    assert set(out["state"]) == set(range(len(params)))
+    for i, p in enumerate(params):
+        got = out["state"][i]["momentum_buffer"]
+        exp = sd["state"][i]["momentum_buffer"] if i in sd["state"] else torch.zeros(p.shape)
+        assert got.is_contiguous() and torch.equal(got, exp), i
+    ref2 = torch.optim.SGD(params, lr=1.0)
+    ref2.load_state_dict(out)                                        # and back into the stock optimiser
+    assert ref2.param_groups[0]["momentum"] == 0.9 and torch.equal(ref2.state[params[3]]["momentum_buffer"], out["state"][3]["momentum_buffer"])
+    with pytest.raises(ValueError):
+        bad = {"state": {}, "param_groups": [dict(sd["param_groups"][0], nesterov=True)]}
+        opt.load_state_dict(bad)
+
+
+def test_checkpoint_weights_plus_optimizer_state(cfg_path, tmp_path):
+    import torch
+    from singleshotpose_b200.darknet import Darknet
+    from singleshotpose_b200.optim import FlatSGD
+    from singleshotpose_b200.checkpoint import save_checkpoint, load_checkpoint
+    torch.manual_seed(3)
+    a = Darknet(cfg_path); a._engine.materialize(torch.device("cpu"))
+    oa = FlatSGD(a, lr=1e-4, momentum=0.9, weight_decay=0.032)
+    oa._v = torch.randn(a._engine.flat_params.numel(), generator=torch.Generator().manual_seed(4))
+    a.seen, a.iter = 6400, 100
+    f = str(tmp_path / "ck.weights")
+    save_checkpoint(a, oa, f)
+    torch.manual_seed(9)
+    b = Darknet(cfg_path); b._engine.materialize(torch.device("cpu"))
+    ob = FlatSGD(b, lr=1.0)
+    assert load_checkpoint(b, ob, f) is True
+    assert (b.seen, b.iter) == (6400, 100) and ob.param_groups[0]["momentum"] == 0.9
+    assert torch.equal(ob._v, oa._v)
+    for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.equal(p, q), n
+    os.remove(f + ".optim.pt")
+    with pytest.raises(FileNotFoundError):
+        load_checkpoint(b, ob, f)
+    assert load_checkpoint(b, ob, f, strict=False) is False
