@@ -135,6 +135,27 @@ int ssp_pnp_batched(const float* points3d, int points3d_shared, const float* poi
 int ssp_project_points(const float* X, int rows, int nv, const double* Rt, const double* K3x3, long long n,
                        float* out, void* stream);
 
+/* ---- training-image pipeline: byte-exact with the Pillow routines image.py calls.  Images are device
+ *      uint8 HWC RGB, dense.  resample = PIL.Image.Resampling value (0 NEAREST, 2 BILINEAR, 3 BICUBIC = resize()'s default
+ *      in Pillow >= 7).  `work` is caller-provided device scratch (16-B aligned) of at least *_work_bytes() bytes.
+ *  ssp_aug_resize_u8: Image.crop((x0, y0, x0+in_w, y0+in_h)).resize((out_w, out_h), resample) (image.py:64,69; dataset.py:103);
+ *      the crop window may stick out of the source (zero fill), pass (0, 0, src_w, src_h) for a plain resize.
+ *  ssp_aug_rgb2hsv_u8 / hsv2rgb_u8: Image.convert('HSV') / ('RGB') (image.py:15,30).
+ *  ssp_aug_sample: change_background (image.py:110-127) -> crop -> resize -> distort_image (image.py:14-32) -> ToTensor
+ *      (dataset.py transform) for one sample.  luts = 5 x 256 bytes: posmask, negmask (image.py:121-122), hue, saturation,
+ *      value (image.py:17-27) point() tables, built by the host exactly as Image.point() builds them.  Crop window
+ *      (pleft, ptop, cw, ch) with cw = swidth - 1, ch = sheight - 1 (image.py:64).  out_u8 (HWC) and out_chw (float32
+ *      CHW in [0,1]) are both optional, at least one required. ---- */
+long long ssp_aug_resize_work_bytes(int in_w, int in_h, int out_w, int out_h, int resample);
+int ssp_aug_resize_u8(const void* src, int src_w, int src_h, int x0, int y0, int in_w, int in_h, void* dst, int out_w,
+                      int out_h, int resample, void* work, long long work_bytes, void* stream);
+int ssp_aug_rgb2hsv_u8(const void* rgb, void* hsv, long long n_pixels, void* stream);
+int ssp_aug_hsv2rgb_u8(const void* hsv, void* rgb, long long n_pixels, void* stream);
+long long ssp_aug_sample_work_bytes(int ow, int oh, int bw, int bh, int cw, int ch, int out_w, int out_h, int resample);
+int ssp_aug_sample(const void* img, const void* mask, int ow, int oh, const void* bg, int bw, int bh, const void* luts,
+                   int pleft, int ptop, int cw, int ch, int out_w, int out_h, int resample, void* work,
+                   long long work_bytes, void* out_u8_or_null, float* out_chw_or_null, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

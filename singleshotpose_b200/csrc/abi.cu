@@ -45,6 +45,12 @@ int region_loss_multi_fwd_bwd(const float*, const float*, float*, double*, int, 
 int region_decode_multi(const float*, int, int, int, int, int, int, int, int, float*, float*, float*, float*, long long*, float*, float*, cudaStream_t);
 int pnp_batched(const float*, int, const float*, const float*, int, long long, int, double*, double*, int*, cudaStream_t);
 int project_points(const float*, int, int, const double*, const double*, long long, float*, cudaStream_t);
+long long aug_resize_work_bytes(int, int, int, int, int);
+long long aug_sample_work_bytes(int, int, int, int, int, int, int, int, int);
+int aug_resize_u8(const uint8_t*, int, int, int, int, int, int, uint8_t*, int, int, int, uint8_t*, long long, cudaStream_t);
+int aug_convert_u8(const uint8_t*, uint8_t*, long long, int, cudaStream_t);
+int aug_sample(const uint8_t*, const uint8_t*, int, int, const uint8_t*, int, int, const uint8_t*, int, int, int, int, int, int, int, uint8_t*,
+               long long, uint8_t*, float*, cudaStream_t);
 }  // namespace ssp
 
 using namespace ssp;
@@ -143,5 +149,20 @@ int ssp_pnp_batched(const float* P3, int shared, const float* uv, const float* K
 }
 int ssp_project_points(const float* X, int rows, int nv, const double* Rt, const double* K, long long n, float* out, void* s) {
   return project_points(X, rows, nv, Rt, K, n, out, ST(s));
+}
+long long ssp_aug_resize_work_bytes(int in_w, int in_h, int out_w, int out_h, int resample) { return aug_resize_work_bytes(in_w, in_h, out_w, out_h, resample); }
+int ssp_aug_resize_u8(const void* src, int src_w, int src_h, int x0, int y0, int in_w, int in_h, void* dst, int out_w, int out_h, int resample,
+                      void* work, long long work_bytes, void* s) {
+  return aug_resize_u8((const uint8_t*)src, src_w, src_h, x0, y0, in_w, in_h, (uint8_t*)dst, out_w, out_h, resample, (uint8_t*)work, work_bytes, ST(s));
+}
+int ssp_aug_rgb2hsv_u8(const void* rgb, void* hsv, long long n_pixels, void* s) { return aug_convert_u8((const uint8_t*)rgb, (uint8_t*)hsv, n_pixels, 1, ST(s)); }
+int ssp_aug_hsv2rgb_u8(const void* hsv, void* rgb, long long n_pixels, void* s) { return aug_convert_u8((const uint8_t*)hsv, (uint8_t*)rgb, n_pixels, 2, ST(s)); }
+long long ssp_aug_sample_work_bytes(int ow, int oh, int bw, int bh, int cw, int ch, int out_w, int out_h, int resample) {
+  return aug_sample_work_bytes(ow, oh, bw, bh, cw, ch, out_w, out_h, resample);
+}
+int ssp_aug_sample(const void* img, const void* mask, int ow, int oh, const void* bg, int bw, int bh, const void* luts, int pleft, int ptop, int cw,
+                   int ch, int out_w, int out_h, int resample, void* work, long long work_bytes, void* out_u8, float* out_chw, void* s) {
+  return aug_sample((const uint8_t*)img, (const uint8_t*)mask, ow, oh, (const uint8_t*)bg, bw, bh, (const uint8_t*)luts, pleft, ptop, cw, ch, out_w, out_h,
+                    resample, (uint8_t*)work, work_bytes, (uint8_t*)out_u8, out_chw, ST(s));
 }
 }

@@ -6,7 +6,9 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["abi.cu", "conv_tc.cu", "conv_tc2.cu", "conv_band.cu", "wgrad_tc.cu", "conv_simt.cu", "conv0_direct.cu", "elementwise.cu", "region.cu", "region_multi.cu", "pnp.cu"]
+SOURCES = ["abi.cu", "conv_tc.cu", "conv_tc2.cu", "conv_band.cu", "wgrad_tc.cu", "conv_simt.cu", "conv0_direct.cu", "elementwise.cu", "region.cu", "region_multi.cu", "pnp.cu", "augment.cu"]
+# augment.cu restates Pillow's float/double pixel arithmetic bit for bit: no multiply-add contraction there
+EXTRA = {"augment.cu": ["-fmad=false"]}
 LIB = os.path.join(HERE, "libssp_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -17,7 +19,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cu", ".cuh"))]
+    deps = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".h"))]
     deps.append(os.path.join(HERE, "..", "..", "include", "ssp_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -30,7 +32,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(HERE, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(HERE, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, *EXTRA.get(src, []), "-c", os.path.join(HERE, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

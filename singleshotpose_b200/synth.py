@@ -91,3 +91,37 @@ def pnp_problems(n, sigma=0.5, seed=5, with_center=True):
     uv = np.stack([K[0, 0] * Pc[..., 0] / Pc[..., 2] + K[0, 2], K[1, 1] * Pc[..., 1] / Pc[..., 2] + K[1, 2]], -1)
     uv = uv + rng.normal(size=uv.shape) * sigma
     return dict(P3=P3, uv=uv.astype(np.float32), K=K.astype(np.float32), R=R, t=t)
+
+
+def photo_sample(seed, ow=640, oh=480, bw=500, bh=375):
+    """One synthetic training sample for the image pipeline (image.py:129-142): (image, object mask, background), uint8 HxWx3 RGB.
+    Integer arithmetic only, so every platform generates the same bytes.  The mask is an ellipse (255 inside, 0 outside) with
+    an anti-aliased rim of intermediate values, like the LINEMOD masks after PNG decoding."""
+    rng = np.random.default_rng(1000 + seed)
+    yy, xx = np.mgrid[0:oh, 0:ow]
+    base = np.stack([xx * 255 // max(ow - 1, 1), yy * 255 // max(oh - 1, 1), (xx + yy) * 255 // max(ow + oh - 2, 1)], -1)
+    img = np.clip(base + rng.integers(-48, 49, (oh, ow, 3)), 0, 255).astype(np.uint8)
+    cx, cy = int(rng.integers(ow // 4, 3 * ow // 4)), int(rng.integers(oh // 4, 3 * oh // 4))
+    ax, ay = int(rng.integers(ow // 8, ow // 3)), int(rng.integers(oh // 8, oh // 3))
+    d = ((xx - cx) * ay) ** 2 + ((yy - cy) * ax) ** 2                       # < (ax*ay)^2 inside the ellipse
+    r2 = (ax * ay) ** 2
+    m = np.where(d < r2 * 9 // 10, 255, np.where(d < r2, rng.integers(0, 256, (oh, ow)), 0)).astype(np.uint8)
+    mask = np.repeat(m[:, :, None], 3, 2)
+    by, bx = np.mgrid[0:bh, 0:bw]
+    bbase = np.stack([255 - bx * 255 // max(bw - 1, 1), (bx * by) % 256, by * 255 // max(bh - 1, 1)], -1)
+    bg = np.clip(bbase + rng.integers(-64, 65, (bh, bw, 3)), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(img), np.ascontiguousarray(mask), np.ascontiguousarray(bg)
+
+
+def label_rows(seed, n=1, num_keypoints=9):
+    """n label rows [cls, x0, y0, ..., x8, y8, xrange, yrange] like the reference's labels/*.txt"""
+    rng = np.random.default_rng(2000 + seed)
+    rows = np.zeros((n, 2 * num_keypoints + 3))
+    for r in rows:
+        c = rng.uniform(0.2, 0.8, 2)
+        pts = c + rng.uniform(-0.15, 0.15, (num_keypoints, 2))
+        pts[0] = c
+        r[0] = 0
+        r[1:1 + 2 * num_keypoints] = pts.reshape(-1)
+        r[-2:] = pts.max(0) - pts.min(0)
+    return rows

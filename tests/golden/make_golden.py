@@ -236,7 +236,62 @@ def main_multi():
     print("multi decode golden: boxes per image", counts)
 
 
+AUG_CASES = [  # seed, (ow, oh), (bw, bh), network shape
+    (0, (160, 120), (100, 75), (96, 96)),
+    (1, (160, 120), (211, 97), (128, 128)),
+    (2, (320, 240), (250, 187), (224, 224)),
+    (3, (96, 128), (64, 64), (160, 160)),
+]
+
+
+def main_augment():
+    """image pipeline (image.py): the reference's change_background + data_augmentation + fill_truth_detection run UNMODIFIED on
+    synthetic samples with a seeded `random`.  One shim: Pillow 12 renamed ImageMath.eval (image.py:124) to unsafe_eval."""
+    import random
+    import tempfile
+    from PIL import Image, ImageMath
+    from oracle import augment_ref as A
+    if not hasattr(ImageMath, "eval"):
+        ImageMath.eval = ImageMath.unsafe_eval
+    sys.path.insert(0, REF)
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        import image as refimage
+    finally:
+        os.chdir(cwd)
+    out = {}
+    for seed, (ow, oh), (bw, bh), shape in AUG_CASES:
+        img, mask, bg = synth.photo_sample(seed, ow, oh, bw, bh)
+        rows = synth.label_rows(seed, n=1 + seed % 2)
+        random.seed(seed)
+        comp = refimage.change_background(Image.fromarray(img), Image.fromarray(mask), Image.fromarray(bg))
+        res, flip, dx, dy, sx, sy = refimage.data_augmentation(comp, shape, 0.2, 0.1, 1.5, 1.5)
+        with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+            np.savetxt(f, rows)
+        label = refimage.fill_truth_detection(f.name, shape[0], shape[1], flip, dx, dy, 1. / sx, 1. / sy, 9, 50)
+        os.unlink(f.name)
+        res = np.asarray(res)
+        # the oracle restatement, same seed
+        o_img, o_flip, o_dx, o_dy, o_sx, o_sy = A.data_augmentation(A.change_background(img, mask, bg), shape, 0.2, 0.1, 1.5, 1.5,
+                                                                    rng=random.Random(seed))
+        assert np.array_equal(o_img, res) and (o_flip, o_dx, o_dy, o_sx, o_sy) == (flip, dx, dy, sx, sy), seed
+        assert np.array_equal(A.fill_truth_detection(rows, flip, dx, dy, 1. / sx, 1. / sy, 9, 50), label)
+        out["img_%d" % seed] = res
+        out["comp_%d" % seed] = np.asarray(comp)
+        out["xform_%d" % seed] = np.array([flip, dx, dy, sx, sy], np.float64)
+        out["label_%d" % seed] = label
+        print("augment golden seed %d: %s -> %s, oracle byte-identical" % (seed, (ow, oh), shape))
+    import PIL
+    out["pillow_version"] = np.array(PIL.__version__)
+    np.savez_compressed(os.path.join(HERE, "augment.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--augment-only" in sys.argv:
+        main_augment()
+        sys.exit(0)
     if "--multi-only" not in sys.argv:
         main()
     main_multi()
+    main_augment()
