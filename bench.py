@@ -391,6 +391,20 @@ def main():
             infer["batch%d" % bsz] = {"ms": msi, "images_per_s": bsz / (msi * 1e-3)}
         infer["what"] = "eval-mode forward (running-stat BN) + per-image decode + PnP, eager launches, inputs resident in HBM"
         model.train()
+    # ---------------- training-image pipeline (image.py): GPU vs the PIL calls of the reference ----------------
+    augment = None
+    if world == 1 and not args.no_pnp:
+        try:
+            augment = augment_extra(dev, e0, e1)
+        except Exception as ex:                                  # an extra must not take the headline line down; say why
+            augment = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    # ---------------- multi-object head (BASELINE.json configs[3]): yolo-pose-multi.cfg, batch 32 ----------------
+    multi = None
+    if world == 1 and not args.no_pnp:
+        try:
+            multi = multi_extra(dev, e0, e1)
+        except Exception as ex:
+            multi = {"error": "%s: %s" % (type(ex).__name__, ex)}
     out = {
         "metric": "images/sec fwd+bwd+SGD (416x416, yolo-pose.cfg)", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -402,12 +416,109 @@ def main():
         "gpu_launches": launches, "clocks": clocks,
         "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e / args.steps,
                 "h2d_bytes_per_step": x_host.numel() * 4 + t_host.numel() * 4, "d2h_bytes_per_step": 4},
-        "roofline": roofline, "cpu_baseline": cpu, "pnp": pnp, "inference": infer,
+        "roofline": roofline, "cpu_baseline": cpu, "pnp": pnp, "inference": infer, "augment": augment, "multi": multi,
     }
     print(json.dumps(out))
     sys.stdout.flush()
     if world > 1:
         os._exit(0)
+
+
+def augment_extra(dev, e0, e1, B=64):
+    """change_background + data_augmentation + ToTensor of image.py for one training batch: 64 synthetic 640x480 LINEMOD-sized
+    images + masks, 500x375 VOC-sized backgrounds -> (64,3,416,416) float32.  GPU: GpuAugmenter end to end (host byte arrays ->
+    pinned staging -> one H2D copy -> kernels), CUDA events.  CPU: the same PIL calls the reference makes, 1 thread, 8 samples."""
+    import random
+    import numpy as np
+    import torch
+    from singleshotpose_b200 import image as I, synth
+    samples = [synth.photo_sample(i) for i in range(8)]
+    imgs, masks, bgs = [[s[k] for s in samples] * (B // 8) for k in range(3)]
+    aug = I.GpuAugmenter(dev)
+    rng = random.Random(0)
+    for _ in range(3):
+        x, params = aug(imgs, masks, bgs, (416, 416), rng=rng)
+    torch.cuda.synchronize()
+    reps = 5
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(reps):
+        x, params = aug(imgs, masks, bgs, (416, 416), rng=rng)
+    e1.record(); torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / reps
+    ms = e0.elapsed_time(e1) / reps
+    res = {"images_per_s": B / wall, "ms_per_batch_wall": wall * 1e3, "ms_per_batch_device_span": ms, "batch": B,
+           "h2d_bytes_per_batch": aug.h2d_bytes, "out_bytes_per_batch": x.numel() * 4,
+           "what": "64 x (640x480 image+mask, 500x375 background) -> 416x416 float32, BICUBIC (Pillow's resize() default), "
+                   "wall time includes host staging (numpy copies into pinned memory, point() tables) and the H2D copy"}
+    try:
+        from PIL import Image
+        lp, ln = I.mask_luts()
+        m = 8
+        t0 = time.perf_counter()
+        for i in range(m):
+            p = params[i]
+            im, mk, bg = (Image.fromarray(a) for a in samples[i])
+            bgr = np.asarray(bg.resize(im.size))
+            comp = np.clip(np.asarray(im).astype(np.int32) * lp[np.asarray(mk)] + bgr.astype(np.int32) * ln[np.asarray(mk)], 0, 255).astype(np.uint8)
+            c = Image.fromarray(comp).crop((p["pleft"], p["ptop"], p["pleft"] + p["cw"], p["ptop"] + p["ch"])).resize((416, 416))
+            h, s, v = c.convert("HSV").split()
+            lh, ls, lv = I.distort_luts(p["dhue"], p["dsat"], p["dexp"])
+            c = Image.merge("HSV", (h.point(list(lh)), s.point(list(ls)), v.point(list(lv)))).convert("RGB")
+            ref = torch.from_numpy(np.asarray(c).copy()).permute(2, 0, 1).float().div(255)
+        res["cpu_pil_images_per_s"] = m / (time.perf_counter() - t0)
+        res["cpu_sample"] = "%d samples, the PIL calls of image.py (resize/crop/convert/point/merge), 1 thread; the numpy mask blend stands in for ImageMath" % m
+        res["last_sample_identical_to_pil"] = bool(torch.equal(ref, x[m - 1].cpu()))
+    except Exception as ex:
+        res["cpu_pil_images_per_s"] = None
+        res["cpu_sample"] = "unavailable: %s" % type(ex).__name__
+    return res
+
+
+def multi_extra(dev, e0, e1, B=32):
+    """configs[3]: yolo-pose-multi.cfg at batch 32 -- eval forward + get_multi_region_boxes (conf_thresh 0.05), and the training
+    step's forward + RegionLoss-multi + backward (1-3 GTs per image)."""
+    import torch
+    from singleshotpose_b200 import synth
+    from singleshotpose_b200.cfgs import write_cfg
+    from singleshotpose_b200.darknet_multi import Darknet as DarknetMulti
+    from singleshotpose_b200.region_loss_multi import RegionLoss as RegionLossMulti
+    from singleshotpose_b200.utils_multi import get_multi_region_boxes
+    torch.manual_seed(0)
+    m = DarknetMulti(write_cfg(multi=True)).to(dev)
+    x = synth.images(B, seed=3).to(dev)
+    tgt = synth.targets_multi(B, seed=5)
+    crit = RegionLossMulti(anchors=m.anchors); crit.verbose = False
+    res = {}
+    m.train()
+    for _ in range(3):
+        for p in m.parameters():
+            p.grad = None
+        crit(m(x), tgt, 20).backward()
+    torch.cuda.synchronize()
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        for p in m.parameters():
+            p.grad = None
+        loss = crit(m(x), tgt, 20)
+        loss.backward()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    res["train_fwd_loss_bwd"] = {"ms": ms, "images_per_s": B / (ms * 1e-3), "loss": float(loss)}
+    m.eval()
+    with torch.no_grad():
+        for _ in range(2):
+            get_multi_region_boxes(m(x), 0.05, 13, 9, m.anchors, 5, 3, only_objectness=0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            boxes = get_multi_region_boxes(m(x), 0.05, 13, 9, m.anchors, 5, 3, only_objectness=0)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+    res["eval_fwd_decode"] = {"ms": dt * 1e3, "images_per_s": B / dt, "boxes": int(sum(len(b) for b in boxes))}
+    res["what"] = "yolo-pose-multi.cfg, batch %d, 416x416 synthetic, eager launches; decode returns the reference's python box lists (wall clock)" % B
+    return res
 
 
 def np_f32():

@@ -33,21 +33,32 @@ def point_lut(fn):
     return np.clip(np.array([round(fn(i)) for i in range(256)], np.int64), 0, 255).astype(np.uint8)
 
 
+_RAMP = np.arange(256, dtype=np.float64)
+
+
+def _store_u8(values):
+    """round() (half to even, like Python's) then saturate to a byte: what Image.point() does with a float table"""
+    return np.clip(np.rint(values), 0, 255).astype(np.uint8)
+
+
+_MASK_LUTS = None
+
+
 def mask_luts():
-    """posmask, negmask of change_background (image.py:121-122)"""
-    return point_lut(lambda i: i / 255), point_lut(lambda i: 1 - i / 255)
+    """posmask, negmask of change_background (image.py:121-122): point(i / 255), point(1 - i / 255)"""
+    global _MASK_LUTS
+    if _MASK_LUTS is None:
+        _MASK_LUTS = (_store_u8(_RAMP / 255), _store_u8(1 - _RAMP / 255))
+    return _MASK_LUTS
 
 
 def distort_luts(hue, sat, val):
-    """hue / saturation / value tables of distort_image (image.py:17-27), including the reference's +-255 hue wrap"""
-    def change_hue(x):
-        x += hue * 255
-        if x > 255:
-            x -= 255
-        if x < 0:
-            x += 255
-        return x
-    return point_lut(change_hue), point_lut(lambda i: i * sat), point_lut(lambda i: i * val)
+    """hue / saturation / value tables of distort_image (image.py:17-27), including the reference's +-255 hue wrap.
+    Vectorised over the 256 entries; the same float64 operations, in the same order, as the reference's lambdas."""
+    x = _RAMP + hue * 255
+    x = np.where(x > 255, x - 255, x)
+    x = np.where(x < 0, x + 255, x)
+    return _store_u8(x), _store_u8(_RAMP * sat), _store_u8(_RAMP * val)
 
 
 def rand_scale(s, rng=_random):

@@ -145,8 +145,12 @@ def test_product_draws_tables_and_labels_follow_the_reference(golden):
         b = A.draw_augmentation(640, 480, 0.2, 0.1, 1.5, 1.5, random.Random(seed))
         assert all(a[k] == b[k] for k in ("pleft", "ptop", "flip", "dhue", "dsat", "dexp"))
         assert (a["cw"], a["ch"]) == (640 - b["pleft"] - b["pright"] - 1, 480 - b["ptop"] - b["pbot"] - 1)
-    for f, g in zip(I.mask_luts() + I.distort_luts(0.07, 1.3, 0.8), A.mask_luts() + A.distort_luts(0.07, 1.3, 0.8)):
-        assert np.array_equal(f, g)
+    r = random.Random(7)
+    cases = [(0.07, 1.3, 0.8), (0.1, 1.5, 1.5), (-0.1, 1 / 1.5, 1 / 1.5), (0, 1, 1), (0.5 / 255, 0.5, 2.5 / 255)]
+    cases += [(r.uniform(-0.1, 0.1), I.rand_scale(1.5, r), I.rand_scale(1.5, r)) for _ in range(300)]
+    for hsv in cases:          # the product builds the point() tables vectorised; the oracle calls the reference's lambdas
+        for f, g in zip(I.mask_luts() + I.distort_luts(*hsv), A.mask_luts() + A.distort_luts(*hsv)):
+            assert np.array_equal(f, g), hsv
     for seed, (ow, oh), _bg, shape in AUG_CASES:
         p = I.draw_augmentation(ow, oh, 0.2, 0.1, 1.5, 1.5, random.Random(seed))
         assert np.array_equal(np.array([p["flip"], p["dx"], p["dy"], p["sx"], p["sy"]]), golden["xform_%d" % seed])
