@@ -164,6 +164,60 @@ def hsv2rgb_u8(hsv):
     return out
 
 
+def _a16(n):
+    return (n + 15) & ~15
+
+
+def _stage_plan(imgs, masks, bgs, params, W, H, resample):
+    """staging layout of one batch: per sample img | mask | bg | 5 tables, each 16-B aligned -> (offsets, total bytes, scratch bytes)"""
+    lib = load()
+    offs, total, work_bytes = [], 0, 0
+    for im, mk, bg, p in zip(imgs, masks, bgs, params):
+        if tuple(mk.shape) != tuple(im.shape):
+            raise ValueError("mask %s and image %s differ in size" % (tuple(mk.shape), tuple(im.shape)))
+        if p["cw"] <= 0 or p["ch"] <= 0:
+            raise ValueError("empty crop window %dx%d" % (p["cw"], p["ch"]))
+        o = {}
+        for k, a in (("img", im), ("mask", mk), ("bg", bg)):
+            o[k] = total
+            total += _a16(int(np.prod(a.shape)))
+        o["luts"] = total
+        total += _a16(5 * 256)
+        offs.append(o)
+        nb = lib.ssp_aug_sample_work_bytes(im.shape[1], im.shape[0], bg.shape[1], bg.shape[0], p["cw"], p["ch"], W, H, resample)
+        if nb < 0:
+            raise SspError("ssp_aug_sample_work_bytes: bad sizes")
+        work_bytes = max(work_bytes, nb)
+    return offs, total, work_bytes
+
+
+_POOL = None
+
+
+def _stage_fill(st, imgs, masks, bgs, params, offs):
+    """copy the batch's bytes and point() tables into the (pinned) staging array `st`; the big copies release the GIL, so a small
+    thread pool moves them in parallel"""
+    global _POOL
+    pos, neg = mask_luts()
+
+    def one(args):
+        im, mk, bg, p, o = args
+        for k, a in (("img", im), ("mask", mk), ("bg", bg)):
+            a = a.cpu().numpy() if torch.is_tensor(a) else a
+            st[o[k]:o[k] + a.size] = a.reshape(-1)
+        lh, ls, lv = distort_luts(p["dhue"], p["dsat"], p["dexp"])
+        st[o["luts"]:o["luts"] + 1280] = np.concatenate([pos, neg, lh, ls, lv])
+    jobs = list(zip(imgs, masks, bgs, params, offs))
+    if len(jobs) < 4:
+        for j in jobs:
+            one(j)
+        return
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=4, thread_name_prefix="ssp-stage")
+    list(_POOL.map(one, jobs))
+
+
 class GpuAugmenter:
     """change_background + data_augmentation + ToTensor for a whole batch: one pinned staging buffer, ONE host->device copy,
     then the per-sample kernels on the current stream, writing straight into the (B,3,H,W) float32 network input.
@@ -188,10 +242,6 @@ class GpuAugmenter:
         self.launches = 0
         self.h2d_bytes = 0
 
-    @staticmethod
-    def _a16(n):
-        return (n + 15) & ~15
-
     def __call__(self, imgs, masks, bgs, shape, jitter=0.2, hue=0.1, saturation=1.5, exposure=1.5, rng=_random, params=None):
         B = len(imgs)
         if not (len(masks) == len(bgs) == B) or B == 0:
@@ -202,25 +252,7 @@ class GpuAugmenter:
         bgs = [_u8_hwc(a, "bg") for a in bgs]
         if params is None:
             params = [draw_augmentation(im.shape[1], im.shape[0], jitter, hue, saturation, exposure, rng) for im in imgs]
-        lib = load()
-        # ---- staging layout: per sample img | mask | bg | 5 tables, each 16-B aligned
-        offs, total, work_bytes = [], 0, 0
-        for im, mk, bg, p in zip(imgs, masks, bgs, params):
-            if tuple(mk.shape) != tuple(im.shape):
-                raise ValueError("mask %s and image %s differ in size" % (tuple(mk.shape), tuple(im.shape)))
-            if p["cw"] <= 0 or p["ch"] <= 0:
-                raise ValueError("empty crop window %dx%d" % (p["cw"], p["ch"]))
-            o = {}
-            for k, a in (("img", im), ("mask", mk), ("bg", bg)):
-                o[k] = total
-                total += self._a16(int(np.prod(a.shape)))
-            o["luts"] = total
-            total += self._a16(5 * 256)
-            offs.append(o)
-            nb = lib.ssp_aug_sample_work_bytes(im.shape[1], im.shape[0], bg.shape[1], bg.shape[0], p["cw"], p["ch"], W, H, self.resample)
-            if nb < 0:
-                raise SspError("ssp_aug_sample_work_bytes: bad sizes")
-            work_bytes = max(work_bytes, nb)
+        offs, total, work_bytes = _stage_plan(imgs, masks, bgs, params, W, H, self.resample)
         if self._stage is None or self._stage.numel() < total:
             self._stage = torch.empty(total, dtype=torch.uint8).pin_memory()
             self._dev = torch.empty(total, dtype=torch.uint8, device=self.device)
@@ -228,14 +260,7 @@ class GpuAugmenter:
             self._work = _work(work_bytes, self.device)
         if self._copied is not None:
             self._copied.synchronize()      # the previous batch's host->device copy has drained the pinned staging buffer
-        st = self._stage.numpy()
-        pos, neg = mask_luts()
-        for im, mk, bg, p, o in zip(imgs, masks, bgs, params, offs):
-            for k, a in (("img", im), ("mask", mk), ("bg", bg)):
-                a = a.cpu().numpy() if torch.is_tensor(a) else a
-                st[o[k]:o[k] + a.size] = a.reshape(-1)
-            lh, ls, lv = distort_luts(p["dhue"], p["dsat"], p["dexp"])
-            st[o["luts"]:o["luts"] + 1280] = np.concatenate([pos, neg, lh, ls, lv])
+        _stage_fill(self._stage.numpy(), imgs, masks, bgs, params, offs)
         self._dev[:total].copy_(self._stage[:total], non_blocking=True)
         self._copied = torch.cuda.Event()
         self._copied.record()

@@ -166,3 +166,32 @@ def test_image_pipeline_has_no_cpu_path():
         I.resize_u8(torch.zeros(4, 4, 3, dtype=torch.uint8), (2, 2))
     with pytest.raises(SspError):
         I.GpuAugmenter("cpu")
+
+
+def test_staging_layout_feeds_the_kernel_core(host):
+    """GpuAugmenter's host half (batch plan, pinned-buffer fill with the thread pool, argument order of ssp_aug_sample) driven
+    into the host build of the kernel core: a mixed-size batch equals the oracle sample by sample."""
+    sizes = [((160, 120), (100, 75)), ((96, 128), (64, 64)), ((200, 150), (333, 41)), ((160, 120), (160, 120)), ((64, 48), (20, 30))]
+    samples = [synth.photo_sample(10 + i, ow, oh, bw, bh) for i, ((ow, oh), (bw, bh)) in enumerate(sizes)]
+    imgs, masks, bgs = zip(*samples)
+    W = H = 104
+    rng = random.Random(100)
+    params = [I.draw_augmentation(im.shape[1], im.shape[0], 0.2, 0.1, 1.5, 1.5, rng) for im in imgs]
+    offs, total, work_bytes = I._stage_plan(imgs, masks, bgs, params, W, H, I.BICUBIC)
+    assert all(o[k] % 16 == 0 for o in offs for k in o) and total % 16 == 0
+    st = np.full(total, 0xAB, np.uint8)
+    I._stage_fill(st, imgs, masks, bgs, params, offs)
+    work = np.empty(work_bytes, np.uint8)
+    rng = random.Random(100)
+    base = st.ctypes.data
+    for i, (im, bg, p, o) in enumerate(zip(imgs, bgs, params, offs)):
+        assert host.h_augment_work_bytes(im.shape[1], im.shape[0], bg.shape[1], bg.shape[0], p["cw"], p["ch"], W, H, 3) <= work_bytes
+        o8 = np.empty((H, W, 3), np.uint8)
+        rc = host.h_augment_sample(C.c_void_p(base + o["img"]), C.c_void_p(base + o["mask"]), im.shape[1], im.shape[0],
+                                   C.c_void_p(base + o["bg"]), bg.shape[1], bg.shape[0], C.c_void_p(base + o["luts"]), p["pleft"], p["ptop"],
+                                   p["cw"], p["ch"], W, H, 3, _p(work), C.c_longlong(work_bytes), _p(o8), None)
+        assert rc == 0
+        want = A.data_augmentation(A.change_background(*samples[i]), (W, H), 0.2, 0.1, 1.5, 1.5, rng=rng)[0]
+        assert np.array_equal(o8, want), i
+    with pytest.raises(ValueError):
+        I._stage_plan(imgs, [m[:10] for m in masks], bgs, params, W, H, I.BICUBIC)
