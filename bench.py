@@ -505,7 +505,7 @@ def multi_extra(dev, e0, e1, B=32):
         loss.backward()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    res["train_fwd_loss_bwd"] = {"ms": ms, "images_per_s": B / (ms * 1e-3), "loss": float(loss)}
+    res["train_fwd_loss_bwd"] = {"ms": ms, "images_per_s": B / (ms * 1e-3), "loss": float(loss.detach())}
     m.eval()
     with torch.no_grad():
         for _ in range(2):
