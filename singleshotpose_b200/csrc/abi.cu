@@ -24,6 +24,7 @@ int conv_gemm_simt(const void*, const void*, long long, int, int, const void*, c
 int conv0_direct(const float*, const float*, const float*, float*, int, double*, double*, int, int, int, cudaStream_t);
 int wgrad_gemm_tc(const void*, long long, int, int, int, const void*, long long, int, int, int, int, int, int, int, float*, int, int, float, cudaStream_t);
 int wgrad_gemm_simt(const void*, long long, int, int, int, const void*, long long, int, int, int, int, int, int, int, float*, int, int, float, cudaStream_t);
+int wgrad_gemm_tc2(const void*, long long, int, int, int, const void*, long long, int, int, int, int, int, int, int, float*, int, int, float, cudaStream_t);
 int pack_input_im2col(const float*, void*, void*, int, int, int, cudaStream_t);
 int pack_nchw(const float*, void*, void*, int, int, int, int, int, int, int, float, cudaStream_t);
 int unpack_nchw(const float*, float*, int, int, int, int, int, int, cudaStream_t);
@@ -101,6 +102,10 @@ int ssp_conv_gemm_bnact(int impl, const void* a_hi, const void* a_lo, long long 
 int ssp_wgrad_gemm(int impl, const void* dy, long long dy_rows, int dy_ld, int cout, int dy_fmt, const void* x, long long x_rows, int x_ld,
                    int cin, int x_fmt, int N, int H, int W, int taps, float* dw, int dw_ld, int cin_store, float scale, void* s) {
   if (impl == SSP_IMPL_SIMT) return wgrad_gemm_simt(dy, dy_rows, dy_ld, cout, dy_fmt, x, x_rows, x_ld, cin, x_fmt, N, H, W, taps, dw, dw_ld, cin_store, scale, ST(s));
+  if (impl == SSP_IMPL_TC2) {      // experimental CTA-pair kernel (opt-in); 1 = layer not eligible -> 1-CTA kernel
+    const int rc = wgrad_gemm_tc2(dy, dy_rows, dy_ld, cout, dy_fmt, x, x_rows, x_ld, cin, x_fmt, N, H, W, taps, dw, dw_ld, cin_store, scale, ST(s));
+    if (rc != 1) return rc;
+  }
   return wgrad_gemm_tc(dy, dy_rows, dy_ld, cout, dy_fmt, x, x_rows, x_ld, cin, x_fmt, N, H, W, taps, dw, dw_ld, cin_store, scale, ST(s));
 }
 int ssp_bn_finalize(double* ssum, double* ssq, double count, const float* gamma, const float* beta, float* rm, float* rv, float momentum,

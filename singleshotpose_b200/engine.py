@@ -162,7 +162,8 @@ class Engine:
         self.use_band = os.environ.get("SSP_BAND", "1") != "0"
         self.fuse_eval = os.environ.get("SSP_FUSE_EVAL", "1") != "0"
         wimpl = os.environ.get("SSP_WGRAD_IMPL", "simt" if impl == "simt" else "tc").lower()
-        self.wgrad_impl = _lib.IMPL_SIMT if wimpl == "simt" else _lib.IMPL_TC
+        # "tc2": experimental CTA-pair weight-gradient kernel (csrc/wgrad_tc2.cu), opt-in until measured on hardware
+        self.wgrad_impl = {"simt": _lib.IMPL_SIMT, "tc2": _lib.IMPL_TC2}.get(wimpl, _lib.IMPL_TC)
         # backward operands: one 16-bit format for dY, W and X (tcgen05 kind::f16 cannot mix fp16 with bf16 -- illegal
         # instruction, measured).  fp16 + a static loss scale (saturating conversion) is 8x more precise than bf16.
         # The activation planes are fp16, so dY and the dgrad weights are fp16 too.

@@ -153,6 +153,30 @@ def test_wgrad_gemm_matches_torch(case, impl, dyfmt):
     assert (out - ref).abs().max() / ref.abs().max() < 1e-4
 
 
+@pytest.mark.skipif(os.environ.get("SSP_EXPERIMENTAL", "0") != "1", reason="experimental CTA-pair wgrad (csrc/wgrad_tc2.cu): opt-in, SSP_EXPERIMENTAL=1")
+@pytest.mark.parametrize("case", [(2, 13, 13, 256, 256, 3), (1, 13, 13, 512, 256, 1), (2, 26, 26, 256, 512, 3), (64, 13, 13, 512, 256, 3)])
+def test_wgrad_pair_experimental(case):
+    """CTA-pair weight gradient vs the 1-CTA tensor-core kernel and torch (eligible shapes: cout, cin multiples of 256)"""
+    N, H, W, cin, cout, k = case
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, cin, H, W, generator=g)
+    dy = torch.randn(N, cout, H, W, generator=g)
+    xh, _, rows = flat_from_nchw(x.to(DEV), fmt=_lib.FMT_F16, split=False)
+    dyh, _, _ = flat_from_nchw(dy.to(DEV), fmt=_lib.FMT_F16, split=False)
+    outs = []
+    for impl in (_lib.IMPL_TC, _lib.IMPL_TC2):
+        dw = torch.zeros(cout, k * k, cin, device=DEV)
+        call("ssp_wgrad_gemm", impl, ptr(dyh), rows, cout, cout, _lib.FMT_F16, ptr(xh), rows, cin, cin, _lib.FMT_F16,
+             N, H, W, k * k, ptr(dw), cin, cin, 1.0, stream_ptr())
+        torch.cuda.synchronize()
+        outs.append(dw)
+    assert (outs[0] - outs[1]).abs().max() / outs[0].abs().max() < 1e-4
+    if N <= 2:
+        ref = torch.nn.grad.conv2d_weight(x.half().double(), (cout, cin, k, k), dy.half().double(), padding=(k - 1) // 2).float()
+        out = outs[1].view(cout, k, k, cin).permute(0, 3, 1, 2).cpu()
+        assert (out - ref).abs().max() / ref.abs().max() < 1e-4
+
+
 def _bn_ref(y, gamma, beta, route):
     """torch reference of BN(train)+leaky(+pool/reorg) and its autograd."""
     z = F.batch_norm(y, None, None, gamma, beta, training=True, eps=1e-4)
