@@ -352,7 +352,6 @@ def main():
         tg = e0.elapsed_time(e1) * 1e-3
         pnp = {"poses_per_s": n / tg, "n": n, "points": 9, "sigma_px": 0.5, "ms": tg * 1e3}
         try:
-            from oracle.pnp_ref import pnp_ref
             import cv2
             m = 2000
             t0 = time.perf_counter()

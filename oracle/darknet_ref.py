@@ -11,7 +11,6 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 
 def _parse(cfgfile):

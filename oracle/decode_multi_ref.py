@@ -3,7 +3,6 @@ Keeps every (cell, anchor) whose confidence exceeds ``conf_thresh`` in (cy, cx, 
 ``correspondingclass`` (running maxima: ``max_conf`` reset per image, ``max_cls_conf`` never reset).  TEST INFRASTRUCTURE ONLY."""
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 

@@ -8,7 +8,6 @@ TEST INFRASTRUCTURE ONLY.
 """
 from __future__ import annotations
 
-import math
 import torch
 
 

@@ -2,7 +2,6 @@
 of the same op computed on the CPU, and tensor-core kernels against their CUDA-core twins."""
 import os
 
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
