@@ -101,6 +101,9 @@ int ssp_bias_grad_nchw(const float* g_nchw, float* dbias, int N, int C, int HW, 
 /* ---- parameters: weight re-pack from the fp32 master [cout][taps][cin]; optim.SGD (train.py:388) ---- */
 int ssp_pack_weights(const float* w, int cout, int taps, int cin, void* fwd_hi, void* fwd_lo, int fwd_ld,
                      void* dgrad, int dgrad_ld, int dgrad_fmt, void* stream);
+/* experimental shared-memory-tiled variant with identical outputs (opt-in, SSP_PACK=v2; see csrc/pack_v2.cu) */
+int ssp_pack_weights_v2(const float* w, int cout, int taps, int cin, void* fwd_hi, void* fwd_lo, int fwd_ld,
+                        void* dgrad, int dgrad_ld, int dgrad_fmt, void* stream);
 int ssp_sgd_step_flat(float* p, const float* g, float* v, long long n, float lr, float momentum,
                       float weight_decay, float grad_scale, void* stream);
 

@@ -36,6 +36,7 @@ SIGNATURES = {
     "ssp_bn_bwd_finalize": [_p, _p, _p, _p, _i, _i, _f, _p],
     "ssp_bias_grad_nchw": [_p, _p, _i, _i, _i, _i, _f, _p],
     "ssp_pack_weights": [_p, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p],
+    "ssp_pack_weights_v2": [_p, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p],
     "ssp_sgd_step_flat": [_p, _p, _p, _ll, _f, _f, _f, _f, _p],
     "ssp_region_loss_fwd_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _f, _p],
     "ssp_region_decode_argmax": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p],

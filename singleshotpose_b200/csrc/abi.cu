@@ -38,6 +38,7 @@ int bn_bwd_apply(const float*, int, const float*, const float*, const float*, co
 int bn_bwd_finalize(double*, double*, float*, float*, int, int, float, cudaStream_t);
 int bias_grad_nchw(const float*, float*, int, int, int, int, float, cudaStream_t);
 int pack_weights(const float*, int, int, int, void*, void*, int, void*, int, int, cudaStream_t);
+int pack_weights_v2(const float*, int, int, int, void*, void*, int, void*, int, int, cudaStream_t);
 int sgd_step_flat(float*, const float*, float*, long long, float, float, float, float, cudaStream_t);
 int region_loss_fwd_bwd(const float*, const float*, float*, double*, int, int, int, int, int, float, float, float, float, int, float, cudaStream_t);
 int region_decode_argmax(const float*, int, int, int, int, int, int, float*, float*, float*, cudaStream_t);
@@ -128,6 +129,9 @@ int ssp_bn_bwd_apply(const float* y, int y_ld, const float* scale, const float* 
 }
 int ssp_bn_bwd_finalize(double* s1, double* s2, float* dgamma, float* dbeta, int C, int accumulate, float scale, void* s) { return bn_bwd_finalize(s1, s2, dgamma, dbeta, C, accumulate, scale, ST(s)); }
 int ssp_bias_grad_nchw(const float* g, float* db, int N, int C, int HW, int accumulate, float scale, void* s) { return bias_grad_nchw(g, db, N, C, HW, accumulate, scale, ST(s)); }
+int ssp_pack_weights_v2(const float* w, int cout, int taps, int cin, void* f_hi, void* f_lo, int ld_f, void* d, int ld_d, int d_fmt, void* s) {
+  return pack_weights_v2(w, cout, taps, cin, f_hi, f_lo, ld_f, d, ld_d, d_fmt, ST(s));
+}
 int ssp_pack_weights(const float* w, int cout, int taps, int cin, void* f_hi, void* f_lo, int ld_f, void* d, int ld_d, int d_fmt, void* s) {
   return pack_weights(w, cout, taps, cin, f_hi, f_lo, ld_f, d, ld_d, d_fmt, ST(s));
 }

@@ -161,6 +161,8 @@ class Engine:
         self.tc2_min_n = int(os.environ.get("SSP_TC2_MIN_N", "128"))
         self.use_band = os.environ.get("SSP_BAND", "1") != "0"
         self.fuse_eval = os.environ.get("SSP_FUSE_EVAL", "1") != "0"
+        # "v2": experimental shared-memory-tiled weight re-pack (csrc/pack_v2.cu), opt-in until measured on hardware
+        self.pack_fn = "ssp_pack_weights_v2" if os.environ.get("SSP_PACK", "v1").lower() == "v2" else "ssp_pack_weights"
         wimpl = os.environ.get("SSP_WGRAD_IMPL", "simt" if impl == "simt" else "tc").lower()
         # "tc2": experimental CTA-pair weight-gradient kernel (csrc/wgrad_tc2.cu), opt-in until measured on hardware
         self.wgrad_impl = {"simt": _lib.IMPL_SIMT, "tc2": _lib.IMPL_TC2}.get(wimpl, _lib.IMPL_TC)
@@ -263,10 +265,10 @@ class Engine:
             off, n, _g = self._slices[id(conv.weight)]
             w = self.flat_params[off:off + n]
             if L.first:    # [32][9][3] -> K = 27 (+5 zeros): a 1-tap GEMM over the im2col'ed input
-                call("ssp_pack_weights", ptr(w), L.cout, 1, 27, ptr(self.w_hi[i]), ptr(self.w_lo[i]), self.w_hi[i].shape[1],
+                call(self.pack_fn, ptr(w), L.cout, 1, 27, ptr(self.w_hi[i]), ptr(self.w_lo[i]), self.w_hi[i].shape[1],
                      None, 0, 0, s)
             else:
-                call("ssp_pack_weights", ptr(w), L.cout, L.taps, L.cin, ptr(self.w_hi[i]), ptr(self.w_lo[i]), self.w_hi[i].shape[1],
+                call(self.pack_fn, ptr(w), L.cout, L.taps, L.cin, ptr(self.w_hi[i]), ptr(self.w_lo[i]), self.w_hi[i].shape[1],
                      ptr(self.w_d[i]), self.w_d[i].shape[1], self.grad_fmt, s)
             self.launches += 1
         self._weights_version = ver

@@ -176,6 +176,24 @@ def test_wgrad_pair_experimental(case):
         assert (out - ref).abs().max() / ref.abs().max() < 1e-4
 
 
+@pytest.mark.skipif(os.environ.get("SSP_EXPERIMENTAL", "0") != "1", reason="experimental tiled weight re-pack (csrc/pack_v2.cu): opt-in, SSP_EXPERIMENTAL=1")
+@pytest.mark.parametrize("shape", [(64, 9, 32), (1024, 9, 512), (20, 1, 1024), (64, 1, 512), (1024, 9, 1280), (32, 1, 27), (130, 9, 70)])
+def test_pack_weights_v2_experimental(shape):
+    """the tiled re-pack writes exactly the bytes of the default kernel (forward hi/lo planes and the transposed dgrad copy)"""
+    cout, taps, cin = shape
+    w = torch.randn(cout, taps, cin, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    ld_f, ld_d = (taps * cin + 7) // 8 * 8, (taps * cout + 7) // 8 * 8
+    outs = []
+    for fn in ("ssp_pack_weights", "ssp_pack_weights_v2"):
+        hi = torch.zeros(cout, ld_f, dtype=torch.float16, device=DEV); lo = torch.zeros_like(hi)
+        d = torch.zeros(cin, ld_d, dtype=torch.float16, device=DEV)
+        call(fn, ptr(w), cout, taps, cin, ptr(hi), ptr(lo), ld_f, ptr(d), ld_d, _lib.FMT_F16, stream_ptr())
+        torch.cuda.synchronize()
+        outs.append((hi, lo, d))
+    for a, b in zip(*outs):
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+
+
 def _bn_ref(y, gamma, beta, route):
     """torch reference of BN(train)+leaky(+pool/reorg) and its autograd."""
     z = F.batch_norm(y, None, None, gamma, beta, training=True, eps=1e-4)
