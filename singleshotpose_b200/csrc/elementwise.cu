@@ -6,6 +6,14 @@
 // 8-B fp16 vectors), consecutive threads on consecutive channels -> fully coalesced rows.
 #include "ssp_common.cuh"
 
+// Occupancy knob for the HBM-bound BN kernels (97-118 registers -> 2 blocks/SM, 23 % warps active, 47-63 % of DRAM peak under
+// ncu): rebuilding with SSP_BN_MINBLOCKS=3 in the environment caps registers at 85 for a third block.  Undefined (default) = no cap.
+#ifdef SSP_BN_MINBLOCKS
+#define SSP_BN_BOUNDS __launch_bounds__(256, SSP_BN_MINBLOCKS)
+#else
+#define SSP_BN_BOUNDS __launch_bounds__(256)
+#endif
+
 namespace ssp {
 
 // ------------------------------------------------------------------------------------------------
@@ -188,7 +196,7 @@ static inline unsigned unit_grid(int C, long long nunits, int per_thread) {
 
 // POOLED = true : unit = one 2x2 window (needed when any destination is DST_POOL)
 template <bool POOLED>
-__global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyParams p) {
+__global__ void SSP_BN_BOUNDS bn_apply_kernel(const BnApplyParams p) {
   const int Hs = POOLED ? p.H / 2 : p.H, Ws = POOLED ? p.W / 2 : p.W;
   UnitWalk wk(p.C, (long long)p.N * Hs * Ws, BN_UNITS_PER_THREAD);
   if (!wk.active) return;
@@ -343,7 +351,7 @@ struct BwdUnit {
 #define BWD_REDUCE_UNITS_PER_THREAD 32
 
 template <int K0, int K1>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
+__global__ void SSP_BN_BOUNDS bn_bwd_reduce_kernel(const BnBwdParams p) {
   extern __shared__ float red[];           // [2][PL][CG*4]
   constexpr bool POOLED = BwdUnit<K0, K1>::POOLED;
   const int Hs = POOLED ? p.H / 2 : p.H, Ws = POOLED ? p.W / 2 : p.W;
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
 }
 
 template <int K0, int K1>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
+__global__ void SSP_BN_BOUNDS bn_bwd_apply_kernel(const BnBwdParams p) {
   constexpr bool POOLED = BwdUnit<K0, K1>::POOLED;
   const int Hs = POOLED ? p.H / 2 : p.H, Ws = POOLED ? p.W / 2 : p.W;
   UnitWalk wk(p.C, (long long)p.N * Hs * Ws, BN_UNITS_PER_THREAD);
