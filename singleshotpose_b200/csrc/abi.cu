@@ -16,7 +16,7 @@ int fail_msg(int code, const char* msg) { snprintf(g_err, sizeof(g_err), "%s", m
 int conv_gemm_tc(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
                  float*, int, long long, int, const float*, double*, double*, cudaStream_t, const FusedAct*);
 int conv_gemm_tc2(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
-                  float*, int, long long, int, const float*, double*, double*, cudaStream_t, const FusedAct*);
+                  float*, int, long long, int, const float*, double*, double*, cudaStream_t, const FusedAct*, const BnBwdFuse*);
 int conv_gemm_band(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
                    float*, int, long long, int, const float*, double*, double*, cudaStream_t);
 int conv_gemm_simt(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
@@ -82,7 +82,7 @@ int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo, long long a_rows
     if (rc != 1) return rc;          // 1 = layer not eligible (weights do not fit): per-tap kernel below
   }
   if (impl == SSP_IMPL_TC2)
-    return conv_gemm_tc2(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s), nullptr);
+    return conv_gemm_tc2(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s), nullptr, nullptr);
   return conv_gemm_tc(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s), nullptr);
 }
 int ssp_conv0_direct(const float* x, const float* w, const float* bias, float* y, int y_ld, double* ssum, double* ssq, int N, int H, int W, void* s) {
@@ -94,11 +94,19 @@ int ssp_conv_gemm_bnact(int impl, const void* a_hi, const void* a_lo, long long 
   FusedAct fa{scale, shift, slope, (uint16_t*)d_hi, (uint16_t*)d_lo, d_ld, d_c0};
   if (impl == SSP_IMPL_TC2)
     return conv_gemm_tc2(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, SSP_FMT_F16, SSP_FMT_F16, N, H, W, taps, cout, nullptr, 0, 0, EPI_BNACT,
-                         nullptr, nullptr, nullptr, ST(s), &fa);
+                         nullptr, nullptr, nullptr, ST(s), &fa, nullptr);
   if (impl == SSP_IMPL_TC || impl == SSP_IMPL_BAND)
     return conv_gemm_tc(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, SSP_FMT_F16, SSP_FMT_F16, N, H, W, taps, cout, nullptr, 0, 0, EPI_BNACT,
                         nullptr, nullptr, nullptr, ST(s), &fa);
   return fail_msg(SSP_ERR_ARG, "ssp_conv_gemm_bnact: tensor-core implementations only");
+}
+int ssp_conv_gemm_dgrad_bnred(const void* dy, long long dy_rows, int dy_ld, int cout, const void* wd, int wd_rows, int wd_ld, int fmt, int N, int H,
+                              int W, int taps, int cin, float* dx, int dx_ld, long long dx_rows, const float* y, int y_ld, const float* scale,
+                              const float* shift, const float* mean, const float* invstd, float slope, int c_begin, int c_end, double* s1,
+                              double* s2, void* s) {
+  BnBwdFuse bw{y, y_ld, scale, shift, mean, invstd, slope, c_begin, c_end, s1, s2};
+  return conv_gemm_tc2(dy, nullptr, dy_rows, dy_ld, cout, wd, nullptr, wd_rows, wd_ld, fmt, fmt, N, H, W, taps, cin, dx, dx_ld, dx_rows, EPI_F32,
+                       nullptr, nullptr, nullptr, ST(s), nullptr, &bw);
 }
 int ssp_wgrad_gemm(int impl, const void* dy, long long dy_rows, int dy_ld, int cout, int dy_fmt, const void* x, long long x_rows, int x_ld,
                    int cin, int x_fmt, int N, int H, int W, int taps, float* dw, int dw_ld, int cin_store, float scale, void* s) {

@@ -175,6 +175,13 @@ class Engine:
         self.fast = os.environ.get("SSP_PRECISION", "parity").lower() == "fast"   # single-term forward (no hi/lo)
         self.launches = 0
         self.overlap = os.environ.get("SSP_OVERLAP", "1") != "0"
+        # experimental (opt-in, not yet measured): the BN-backward reduction of a producer with ONE direct consumer runs in the
+        # epilogue of that consumer's data-gradient GEMM (csrc/conv_tc2.cu MODE 2) instead of as its own pass over Y and dX
+        self.fuse_bnbwd = os.environ.get("SSP_FUSE_BNBWD", "0") == "1"
+        self._direct_producer = {}
+        for Lp in self.layers:
+            if Lp.bn and len(Lp.dests) == 1 and Lp.dests[0][2] == _lib.ROUTE_DIRECT and Lp.cout % 32 == 0 and Lp.cout <= 1024 and Lp.dests[0][1] % 32 == 0:
+                self._direct_producer.setdefault(Lp.dests[0][0], (Lp.index, Lp.dests[0][1]))
         self._side = None
         self.profile = None          # set to [] to record (kind, layer block, algorithmic flops, start event, end event) per GEMM launch
         net = model.blocks[0]
@@ -401,6 +408,7 @@ class Engine:
         else:
             ws, wstream = s, None
         inv = 1.0 / self.grad_scale        # the whole backward chain carries the loss scale; undone where grads are written
+        reduced_in_dgrad = set()           # producers whose S1/S2 were accumulated by their consumer's dgrad epilogue (experimental)
         for L in reversed(self.layers):
             i = L.index
             conv, bn = mods[i]
@@ -415,7 +423,8 @@ class Engine:
                     srcs += [None, 0, 0, _lib.ROUTE_NONE]
                 common = [ptr(B.y[i]), B.y[i].shape[1], ptr(st["scale"]), ptr(st["shift"]), ptr(st["mean"]), ptr(st["invstd"]),
                           ptr(bn.weight.data), N, L.cout, h, w, L.slope, *srcs, ptr(st["s1"]), ptr(st["s2"])]
-                call("ssp_bn_bwd_reduce", *common, s)
+                if i not in reduced_in_dgrad:
+                    call("ssp_bn_bwd_reduce", *common, s)
                 call("ssp_bn_bwd_apply", *common, ptr(dy), dy.shape[1], self.grad_fmt, 1.0, s)
                 call("ssp_bn_bwd_finalize", ptr(st["s1"]), ptr(st["s2"]), ptr(self.grad_view(bn.weight)), ptr(self.grad_view(bn.bias)),
                      L.cout, 0, inv, s)
@@ -432,9 +441,19 @@ class Engine:
                 ev.record(main)                      # dY of this layer is complete
             if not L.first:                          # data gradient first: it is on the critical path of the next layer
                 wd = self.w_d[i]
-                self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cin, L.taps), ptr(dy), None, B.rows[i], dy.shape[1], L.cout, ptr(wd), None,
-                           L.cin, wd.shape[1], self.grad_fmt, self.grad_fmt, N, h, w, L.taps, L.cin, ptr(B.dx[i]), B.dx[i].shape[1], B.rows[i],
-                           _lib.EPI_F32, None, None, None, s)
+                prod = self._direct_producer.get(i) if self.fuse_bnbwd and self._conv_impl(L.cin, L.taps) == _lib.IMPL_TC2 else None
+                if prod is not None:
+                    j, c0 = prod
+                    Lj, stj = self.layers[j], self.stat[j]
+                    self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm_dgrad_bnred", ptr(dy), B.rows[i], dy.shape[1], L.cout, ptr(wd), L.cin, wd.shape[1],
+                               self.grad_fmt, N, h, w, L.taps, L.cin, ptr(B.dx[i]), B.dx[i].shape[1], B.rows[i], ptr(B.y[j]), B.y[j].shape[1],
+                               ptr(stj["scale"]), ptr(stj["shift"]), ptr(stj["mean"]), ptr(stj["invstd"]), Lj.slope, c0, c0 + Lj.cout,
+                               ptr(stj["s1"]), ptr(stj["s2"]), s)
+                    reduced_in_dgrad.add(j)
+                else:
+                    self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cin, L.taps), ptr(dy), None, B.rows[i], dy.shape[1], L.cout,
+                               ptr(wd), None, L.cin, wd.shape[1], self.grad_fmt, self.grad_fmt, N, h, w, L.taps, L.cin, ptr(B.dx[i]),
+                               B.dx[i].shape[1], B.rows[i], _lib.EPI_F32, None, None, None, s)
             if overlap:
                 side.wait_event(ev)
             if L.first:

@@ -116,6 +116,28 @@ def test_eval_fused_epilogue_matches_unfused(cfg_path):
         assert torch.isfinite(o_f).all() and _rel(o_f, o_u) < 2e-5
 
 
+@pytest.mark.skipif(os.environ.get("SSP_EXPERIMENTAL", "0") != "1", reason="experimental BN-backward/dgrad fusion (conv_tc2.cu MODE 2): opt-in, SSP_EXPERIMENTAL=1")
+def test_fused_bn_backward_reduce_experimental(cfg_path):
+    """S1/S2 of a producer accumulated in its consumer's dgrad epilogue vs the separate bn_bwd_reduce pass: same gradients"""
+    torch.manual_seed(4)
+    m = Darknet(cfg_path).cuda().train()
+    eng = m._engine
+    crit = RegionLoss(); crit.verbose = False
+    x, tgt = synth.images(2, seed=8).cuda(), synth.targets(2, seed=9)
+    grads = []
+    for fuse in (False, True):
+        eng.fuse_bnbwd = fuse
+        for p in m.parameters():
+            p.grad = None
+        l0 = eng.launches
+        crit(m(x), tgt, 20).backward()
+        grads.append(([p.grad.detach().clone() for p in m.parameters()], eng.launches - l0))
+    eng.fuse_bnbwd = False
+    assert grads[1][1] < grads[0][1]                               # the fused run skipped bn_bwd_reduce launches
+    for (n, _p), a, b in zip(m.named_parameters(), grads[0][0], grads[1][0]):
+        assert float((a - b).norm() / (a.norm() + 1e-30)) < 1e-4, n
+
+
 def test_sgd_step_matches_torch_optimizer(cfg_path):
     """FlatSGD (one fused kernel) and torch.optim.SGD on the permuted parameter views give the same update."""
     torch.manual_seed(1)

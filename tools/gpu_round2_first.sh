@@ -2,12 +2,14 @@
 # First GPU call of round 2 (≈2 min): answers the three open questions of profiles/r01_experiments.md in one go.
 #  1. does the experimental CTA-pair weight gradient (csrc/wgrad_tc2.cu) pass its parity test?
 #  2. same-box A/B of the training step with SSP_WGRAD_IMPL=tc vs tc2 (graph replay, no CPU baseline, no extras)
-#     (+ one run with the experimental tiled weight re-pack, SSP_PACK=v2)
+#     (+ one run each with the experimental tiled weight re-pack, SSP_PACK=v2, and the BN-backward/dgrad fusion, SSP_FUSE_BNBWD=1)
 #  3. TMA fill rate per SM with own tiles / shared tiles / cluster multicast (tools/probes/mc_probe.cu)
 mkdir -p gpurun_out
-SSP_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_kernels.py -q -k "wgrad_pair or pack_weights_v2" --timeout 200 2>&1 | tail -4
-for impl in tc tc2 tc tc2 v2pack; do
-  if [ $impl = v2pack ]; then export SSP_PACK=v2; w=tc; else w=$impl; fi
+SSP_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_network.py -q -k "wgrad_pair or pack_weights_v2 or fused_bn_backward" --timeout 300 2>&1 | tail -6
+for impl in tc tc2 tc tc2 v2pack bnfuse; do
+  w=$impl
+  if [ $impl = v2pack ]; then export SSP_PACK=v2; w=tc; fi
+  if [ $impl = bnfuse ]; then unset SSP_PACK; export SSP_FUSE_BNBWD=1; w=tc; fi
   SSP_WGRAD_IMPL=$w timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-pnp 2>/dev/null > gpurun_out/ab_$impl.json
   python - "$impl" <<'PY'
 import json, sys
