@@ -164,6 +164,27 @@ def hsv2rgb_u8(hsv):
     return out
 
 
+def _validation_batch(imgs, shape, dev, resample, resize_fn):
+    W, H = int(shape[0]), int(shape[1])
+    out = torch.empty(len(imgs), 3, H, W, dtype=torch.float32, device=dev)
+    for i, a in enumerate(imgs):
+        a = _u8_hwc(a, "img")
+        d = a.to(dev, non_blocking=True) if torch.is_tensor(a) else torch.from_numpy(a).to(dev, non_blocking=True)
+        r = resize_fn(d, (W, H), resample)                    # (H, W, 3) uint8, byte-identical to PIL
+        out[i] = r.permute(2, 0, 1).to(torch.float32).div_(255)      # torchvision ToTensor
+    return out
+
+
+def load_validation_batch(imgs, shape, device, resample=BICUBIC):
+    """The test-mode branch of listDataset.__getitem__ (dataset.py:100-103) + ToTensor for a batch: every image is resized to
+    `shape` = (width, height) with Image.resize's arithmetic on the GPU (ssp_aug_resize_u8) and returned as one float32
+    (B,3,H,W) CUDA tensor in [0,1].  imgs: uint8 HxWx3 RGB arrays / PIL images of any sizes."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise SspError("load_validation_batch needs a CUDA device (no CPU fallback); got %s" % dev)
+    return _validation_batch(imgs, shape, dev, resample, resize_u8)
+
+
 def _a16(n):
     return (n + 15) & ~15
 

@@ -97,3 +97,14 @@ def test_augmenter_batch_mixed_sources_vs_oracle():
     assert torch.equal(x2, x)
     with pytest.raises(ValueError):
         aug(imgs, masks[:2], bgs, (104, 104))
+
+
+def test_validation_batch_matches_oracle():
+    """dataset.py:100-103 (test mode): img.resize(shape) + ToTensor for a batch of differently sized images"""
+    rng = np.random.default_rng(4)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in ((120, 160), (97, 131), (160, 120))]
+    x = I.load_validation_batch(imgs, (104, 104), "cuda")
+    assert x.shape == (3, 3, 104, 104) and x.is_cuda
+    for i, im in enumerate(imgs):
+        assert torch.equal(x[i].cpu(), torch.from_numpy(A.resize_u8(im, (104, 104))).permute(2, 0, 1).float().div(255))
+
