@@ -236,6 +236,27 @@ def main_multi():
     print("multi decode golden: boxes per image", counts)
 
 
+def main_multires():
+    """the reference network at two of the multi-resolution training shapes (dataset.py:66-90) and the 672^2 test shape
+    (yolo-pose.cfg:23-24): train-mode logits of a seeded random-init model, batch 1"""
+    torch.set_num_threads(os.cpu_count())
+    ref_darknet, _rl, _u = ref_import()
+    torch.manual_seed(0)
+    ref_model = ref_darknet.Darknet(os.path.join(REF, "cfg/yolo-pose.cfg"))
+    torch.manual_seed(0)
+    ora_model = RefDarknet(write_cfg())
+    ref_model.train(); ora_model.train()
+    out = {}
+    for (h, w, seed) in ((352, 480, 5), (224, 224, 6), (672, 672, 7)):
+        x = synth.images(1, h, w, seed=seed)
+        with torch.no_grad():
+            o = ref_model(x)
+            assert torch.equal(o, ora_model(x))
+        out["logits_%dx%d" % (h, w)] = o.numpy().copy()
+        print("multires golden %dx%d ->" % (h, w), tuple(o.shape))
+    np.savez_compressed(os.path.join(HERE, "net_multires.npz"), **out)
+
+
 AUG_CASES = [  # seed, (ow, oh), (bw, bh), network shape
     (0, (160, 120), (100, 75), (96, 96)),
     (1, (160, 120), (211, 97), (128, 128)),
@@ -291,7 +312,11 @@ if __name__ == "__main__":
     if "--augment-only" in sys.argv:
         main_augment()
         sys.exit(0)
+    if "--multires-only" in sys.argv:
+        main_multires()
+        sys.exit(0)
     if "--multi-only" not in sys.argv:
         main()
     main_multi()
     main_augment()
+    main_multires()

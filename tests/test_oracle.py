@@ -113,3 +113,18 @@ def test_network_oracle_matches_reference_golden(golden_dir, cfg_path):
     loss.backward()
     gn = np.array([p.grad.double().norm().item() for p in model.parameters()])
     np.testing.assert_allclose(gn, g["grad_norms"], rtol=2e-2)
+
+
+def test_oracle_network_other_resolutions_match_reference_golden(cfg_path, golden_dir):
+    """the oracle network at a multi-resolution training shape and a small one vs the reference's logits (make_golden.py main_multires)"""
+    import torch
+    from oracle.darknet_ref import RefDarknet
+    from singleshotpose_b200 import synth
+    g = np.load(os.path.join(golden_dir, "net_multires.npz"))
+    torch.manual_seed(0)
+    m = RefDarknet(cfg_path).train()
+    for (h, w, seed) in ((352, 480, 5), (224, 224, 6)):
+        with torch.no_grad():
+            o = m(synth.images(1, h, w, seed=seed))
+        assert torch.equal(o, torch.from_numpy(g["logits_%dx%d" % (h, w)]))
+

@@ -5,7 +5,7 @@
 #     (+ one run each with the experimental tiled weight re-pack, SSP_PACK=v2, and the BN-backward/dgrad fusion, SSP_FUSE_BNBWD=1)
 #  3. TMA fill rate per SM with own tiles / shared tiles / cluster multicast (tools/probes/mc_probe.cu)
 mkdir -p gpurun_out
-SSP_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_network.py -q -k "wgrad_pair or pack_weights_v2 or fused_bn_backward" --timeout 300 2>&1 | tail -6
+SSP_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_network.py -q -k "wgrad_pair or pack_weights_v2 or fused_bn_backward or other_resolutions_match" --timeout 300 2>&1 | tail -6
 for impl in tc tc2 tc tc2 v2pack bnfuse; do
   w=$impl
   if [ $impl = v2pack ]; then export SSP_PACK=v2; w=tc; fi
