@@ -9,8 +9,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["abi.cu", "conv_tc.cu", "conv_tc2.cu", "conv_band.cu", "wgrad_tc.cu", "wgrad_tc2.cu", "conv_simt.cu", "conv0_direct.cu", "elementwise.cu", "pack_v2.cu", "region.cu", "region_multi.cu", "pnp.cu", "augment.cu"]
 # augment.cu restates Pillow's float/double pixel arithmetic bit for bit: no multiply-add contraction there
 EXTRA = {"augment.cu": ["-fmad=false"]}
-if os.environ.get("SSP_BN_MINBLOCKS"):        # experiment knob, see elementwise.cu
-    EXTRA["elementwise.cu"] = ["-DSSP_BN_MINBLOCKS=%d" % int(os.environ["SSP_BN_MINBLOCKS"])]
+for _env, _macro in (("SSP_BN_MINBLOCKS", "SSP_BN_MINBLOCKS"), ("SSP_BN_UNITS", "BN_UNITS_PER_THREAD"),
+                     ("SSP_BN_REDUCE_UNITS", "BWD_REDUCE_UNITS_PER_THREAD")):      # experiment knobs, see elementwise.cu
+    if os.environ.get(_env):
+        EXTRA.setdefault("elementwise.cu", []).append("-D%s=%d" % (_macro, int(os.environ[_env])))
 LIB = os.path.join(HERE, "libssp_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -192,7 +192,9 @@ static inline unsigned unit_grid(int C, long long nunits, int per_thread) {
   const long long per = (long long)PL * per_thread;
   return (unsigned)(((nunits + per - 1) / per) * cblocks);
 }
+#ifndef BN_UNITS_PER_THREAD      // build-time sweep knob (SSP_BN_UNITS=n python csrc/build.py); 8 is the measured default
 #define BN_UNITS_PER_THREAD 8
+#endif
 
 // POOLED = true : unit = one 2x2 window (needed when any destination is DST_POOL)
 template <bool POOLED>
@@ -348,7 +350,9 @@ struct BwdUnit {
   }
 };
 
+#ifndef BWD_REDUCE_UNITS_PER_THREAD   // build-time sweep knob (SSP_BN_REDUCE_UNITS=n); 32 is the measured default
 #define BWD_REDUCE_UNITS_PER_THREAD 32
+#endif
 
 template <int K0, int K1>
 __global__ void SSP_BN_BOUNDS bn_bwd_reduce_kernel(const BnBwdParams p) {
