@@ -16,8 +16,8 @@ algorithms:
   * Image.convert('HSV') / ('RGB') -> rgb2hsv_row / hsv2rgb (libImaging/Convert.c).
   * Image.point(callable) -> 256-entry table, round()ed then clipped to 8 bits (Image.py, _imaging.c getlist).
   * Image.crop outside the image -> zero fill.
-Pinned: tests/test_oracle.py checks every function bit-exactly against the installed Pillow (HSV both ways over all 2^24
-colours) and against the reference's own image.py functions run unmodified (goldens from tests/golden/make_golden.py).
+Pinned: tests/test_augment_cpu.py checks every function bit-exactly against the installed Pillow (HSV both ways over every 7th of the 2^24
+colours, all of them with SSP_FULL_HSV=1 -- 0 mismatches) and against the reference's own image.py functions run unmodified (goldens from tests/golden/make_golden.py).
 Two Pillow-version dependences are inherited, not chosen: resize()'s default filter (BICUBIC since Pillow 7, NEAREST before)
 and point()'s round() (truncation before Pillow 8.3); `resample=` selects the former explicitly.
 """

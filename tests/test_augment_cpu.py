@@ -65,8 +65,15 @@ def _host_resize(lib, img, size, rs, box=None):
 
 
 # ------------------------------------------------------------------------------------------------ oracle vs Pillow / reference
-def test_oracle_hsv_all_colours_vs_pillow(pil):
-    rgb = _all_colours().reshape(4096, 4096, 3)
+def test_oracle_hsv_vs_pillow(pil):
+    """numpy oracle vs Pillow's convert(): every 7th of the 2^24 byte triples (2.4 M colours, all residues of r, g, b) by default,
+    all of them with SSP_FULL_HSV=1 (~1 min; zero mismatches when the oracle was written).  The kernel arithmetic itself
+    (augment_core.h) is checked over ALL triples below -- it is C and takes seconds."""
+    rgb = _all_colours()
+    if os.environ.get("SSP_FULL_HSV", "0") != "1":
+        rgb = np.ascontiguousarray(rgb[::7])
+    n = rgb.shape[0]
+    rgb = rgb[: n - n % 1024].reshape(-1, 1024, 3)
     assert np.array_equal(A.rgb2hsv_u8(rgb), np.asarray(pil.fromarray(rgb, "RGB").convert("HSV")))
     assert np.array_equal(A.hsv2rgb_u8(rgb), np.asarray(pil.fromarray(rgb, "HSV").convert("RGB")))
 
