@@ -3,6 +3,8 @@ one-ground-truth label rows in the reference's 50x21 layout (dataset.py:107 / re
 box-corner 3-D models and exact/noisy 2-D projections for PnP."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -125,3 +127,36 @@ def label_rows(seed, n=1, num_keypoints=9):
         r[1:1 + 2 * num_keypoints] = pts.reshape(-1)
         r[-2:] = pts.max(0) - pts.min(0)
     return rows
+
+
+def write_linemod_like(root, n=4, ow=160, oh=120, num_bg=3):
+    """A tiny dataset tree with the reference's path conventions (image.py:130-131, train.py:309): JPEGImages/00000i.png, mask/000i.png,
+    labels/00000i.txt, a background folder and the list file.  PNG throughout (lossless, so every decoder yields the same bytes).
+    Returns (list file path, background file names)."""
+    from PIL import Image
+    base = os.path.join(root, "LINEMOD", "ape")
+    for d in ("JPEGImages", "mask", "labels"):
+        os.makedirs(os.path.join(base, d), exist_ok=True)
+    bgdir = os.path.join(root, "VOCdevkit", "VOC2012", "JPEGImages")
+    os.makedirs(bgdir, exist_ok=True)
+    lines = []
+    for i in range(n):
+        img, mask, _bg = photo_sample(50 + i, ow, oh, 8, 8)
+        name = "%06d" % i
+        Image.fromarray(img).save(os.path.join(base, "JPEGImages", name + ".png"))
+        Image.fromarray(mask).save(os.path.join(base, "mask", "%04d.png" % i))
+        rows = label_rows(50 + i, n=1 + i % 2)
+        with open(os.path.join(base, "labels", name + ".txt"), "w") as f:
+            if i != 3:                                   # sample 3 has an empty label file (os.path.getsize == 0 branch)
+                np.savetxt(f, rows)
+        lines.append(os.path.join(base, "JPEGImages", name + ".png"))
+    bgs = []
+    for j in range(num_bg):
+        _i, _m, bg = photo_sample(70 + j, 8, 8, 100 + 13 * j, 75 + 7 * j)
+        pth = os.path.join(bgdir, "bg%d.png" % j)
+        Image.fromarray(bg).save(pth)
+        bgs.append(pth)
+    listfile = os.path.join(root, "train.txt")
+    with open(listfile, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return listfile, bgs

@@ -257,6 +257,46 @@ def main_multires():
     np.savez_compressed(os.path.join(HERE, "net_multires.npz"), **out)
 
 
+def main_dataset():
+    """dataset.py: the reference's listDataset (train mode incl. the multi-resolution schedule, and test mode) run UNMODIFIED on a
+    tiny synthetic dataset tree, seeded `random`; outputs = what the DataLoader's default collate would stack."""
+    import random
+    import tempfile
+    from PIL import ImageMath
+    if not hasattr(ImageMath, "eval"):
+        ImageMath.eval = ImageMath.unsafe_eval
+    sys.path.insert(0, REF)
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import dataset as refdataset
+    finally:
+        os.chdir(cwd)
+    to_tensor = lambda img: torch.from_numpy(np.asarray(img).copy()).permute(2, 0, 1).float().div(255)       # transforms.ToTensor
+    out = {}
+    with tempfile.TemporaryDirectory() as root:
+        listfile, bgs = synth.write_linemod_like(root)
+        for tag, seen in (("early", 0), ("late", 10 ** 6)):                 # "late": past 70 epochs -> randint(0,19)+7 cells
+            random.seed(6)
+            ds = refdataset.listDataset(listfile, shape=(96, 96), shuffle=True, transform=to_tensor, train=True, seen=seen, batch_size=2,
+                                        num_workers=2, cell_size=8, bg_file_names=bgs)
+            for i in range(4):
+                img, label = ds[i]
+                out["train_%s_img_%d" % (tag, i)] = (img * 255).round().to(torch.uint8).permute(1, 2, 0).numpy()
+                assert torch.equal(torch.from_numpy(out["train_%s_img_%d" % (tag, i)]).permute(2, 0, 1).float().div(255), img)
+                out["train_%s_label_%d" % (tag, i)] = label.numpy()
+            out["train_%s_seen" % tag] = np.array(ds.seen)
+        random.seed(9)
+        ds = refdataset.listDataset(listfile, shape=(64, 48), shuffle=False, transform=to_tensor, train=False, num_workers=3)
+        for i in range(4):
+            img, label = ds[i]
+            out["test_img_%d" % i] = (img * 255).round().to(torch.uint8).permute(1, 2, 0).numpy()
+            out["test_label_%d" % i] = label.numpy()
+    np.savez_compressed(os.path.join(HERE, "dataset.npz"), **out)
+    print("dataset golden:", sorted(k for k in out if k.endswith("_0")), [out["train_late_img_%d" % i].shape for i in range(4)])
+
+
 AUG_CASES = [  # seed, (ow, oh), (bw, bh), network shape
     (0, (160, 120), (100, 75), (96, 96)),
     (1, (160, 120), (211, 97), (128, 128)),
@@ -312,6 +352,9 @@ if __name__ == "__main__":
     if "--augment-only" in sys.argv:
         main_augment()
         sys.exit(0)
+    if "--dataset-only" in sys.argv:
+        main_dataset()
+        sys.exit(0)
     if "--multires-only" in sys.argv:
         main_multires()
         sys.exit(0)
@@ -320,3 +363,4 @@ if __name__ == "__main__":
     main_multi()
     main_augment()
     main_multires()
+    main_dataset()

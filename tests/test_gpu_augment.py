@@ -108,3 +108,28 @@ def test_validation_batch_matches_oracle():
     for i, im in enumerate(imgs):
         assert torch.equal(x[i].cpu(), torch.from_numpy(A.resize_u8(im, (104, 104))).permute(2, 0, 1).float().div(255))
 
+
+def test_dataset_collate_matches_reference_golden(golden_dir, tmp_path):
+    """listDataset (host half) + GpuCollate (device half) vs the reference's listDataset + ToTensor outputs (golden/dataset.npz)"""
+    from singleshotpose_b200 import dataset as D
+    g = np.load(os.path.join(golden_dir, "dataset.npz"))
+    listfile, bgs = synth.write_linemod_like(str(tmp_path))
+    collate = D.GpuCollate("cuda")
+    random.seed(6)
+    ds = D.listDataset(listfile, shape=(96, 96), shuffle=True, train=True, seen=10 ** 6, batch_size=2, num_workers=2, cell_size=8,
+                       bg_file_names=bgs)
+    samples = [ds[i] for i in range(4)]
+    for b in (0, 2):
+        data, target = collate(samples[b:b + 2])
+        assert data.is_cuda and not target.is_cuda and target.dtype == torch.float64
+        for j in range(2):
+            want = torch.from_numpy(g["train_late_img_%d" % (b + j)]).permute(2, 0, 1).float().div(255)
+            assert torch.equal(data[j].cpu(), want), (b, j)
+            assert np.array_equal(target[j].numpy(), g["train_late_label_%d" % (b + j)])
+    random.seed(9)
+    dt = D.listDataset(listfile, shape=(64, 48), shuffle=False, train=False, num_workers=3)
+    data, target = collate([dt[i] for i in range(4)])
+    for i in range(4):
+        assert torch.equal(data[i].cpu(), torch.from_numpy(g["test_img_%d" % i]).permute(2, 0, 1).float().div(255))
+        assert np.array_equal(target[i].numpy(), g["test_label_%d" % i])
+
