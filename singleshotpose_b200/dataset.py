@@ -25,24 +25,7 @@ import torch
 from torch.utils.data import Dataset
 
 from . import image as _image
-
-
-def read_truths(lab_path, num_keypoints=9):
-    """utils.py:299-306"""
-    num_labels = 2 * num_keypoints + 3
-    if os.path.getsize(lab_path):
-        truths = np.loadtxt(lab_path)
-        return truths.reshape(truths.size // num_labels, num_labels)
-    return np.array([])
-
-
-def read_truths_args(lab_path, num_keypoints=9):
-    """utils.py:308-315: class + 2K keypoint coordinates of every row, flattened (the two range columns are dropped)"""
-    num_labels = 2 * num_keypoints + 1
-    truths = read_truths(lab_path, num_keypoints)
-    if truths.size == 0:
-        return np.array([])
-    return np.ascontiguousarray(truths[:, :num_labels]).reshape(-1)
+from .utils_host import read_truths, read_truths_args          # noqa: F401  (dataset.py:12 imports them from utils)
 
 
 def label_path(imgpath):

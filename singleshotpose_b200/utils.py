@@ -11,6 +11,9 @@ import numpy as np
 import torch
 
 from ._lib import call, ptr, stream_ptr, SspError
+from .utils_host import (makedirs, get_all_files, calc_pts_diameter, adi, get_2d_bb, compute_2d_bb, compute_2d_bb_from_orig_pix,  # noqa: F401
+                         corner_confidences, corner_confidence, sigmoid, softmax, fix_corner_order, read_truths, read_truths_args,
+                         read_pose, load_class_names, image2torch, read_data_cfg, scale_bboxes, file_lines, get_image_size, logging)
 
 
 def _dev():

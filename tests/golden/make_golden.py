@@ -297,6 +297,50 @@ def main_dataset():
     print("dataset golden:", sorted(k for k in out if k.endswith("_0")), [out["train_late_img_%d" % i].shape for i in range(4)])
 
 
+def check_host_helpers():
+    """not a golden: asserts, while /root/reference is at hand, that the host helpers of singleshotpose_b200/utils_host.py return
+    exactly what the reference's utils.py functions return on the same inputs (tests/test_utils_host.py re-checks known answers)."""
+    import tempfile
+    from PIL import Image
+    from singleshotpose_b200 import utils_host as H
+    _d, _rl, R = ref_import()
+    rng = np.random.default_rng(0)
+    pts = rng.normal(size=(700, 3))
+    assert H.calc_pts_diameter(pts) == R.calc_pts_diameter(pts)
+    assert H.adi(pts[:300], pts[300:]) == R.adi(pts[:300], pts[300:])
+    box = list(rng.random(18)); p2 = rng.random((2, 9)) * 400
+    assert H.get_2d_bb(box, 13) == R.get_2d_bb(box, 13) and H.compute_2d_bb(p2) == R.compute_2d_bb(p2)
+    assert H.compute_2d_bb_from_orig_pix(p2, 13) == R.compute_2d_bb_from_orig_pix(p2, 13)
+    g, q = torch.rand(18, 50), torch.rand(18, 50) * 0.2 + 0.4
+    assert torch.equal(H.corner_confidences(g.clone(), q.clone()), R.corner_confidences(g.clone(), q.clone()))
+    assert torch.equal(H.corner_confidence(list(g[:, 0]), q[:, 0].clone()), R.corner_confidence(list(g[:, 0]), q[:, 0].clone()))
+    assert H.sigmoid(0.3) == R.sigmoid(0.3) and torch.equal(H.softmax(g[:, 1]), R.softmax(g[:, 1]))
+    c = rng.random((9, 2)).astype("float32")
+    assert np.array_equal(H.fix_corner_order(c), R.fix_corner_order(c))
+    with tempfile.TemporaryDirectory() as d:
+        listfile, bgs = synth.write_linemod_like(d)
+        lab = listfile.replace("train.txt", os.path.join("LINEMOD", "ape", "labels", "000001.txt"))
+        assert np.array_equal(H.read_truths(lab), R.read_truths(lab)) and np.array_equal(H.read_truths_args(lab), R.read_truths_args(lab))
+        assert np.array_equal(H.read_pose(lab), R.read_pose(lab))
+        assert sorted(H.get_all_files(d)) == sorted(R.get_all_files(d)) and H.get_all_files(d) == R.get_all_files(d)
+        assert H.file_lines(listfile) == R.file_lines(listfile) == 4 and H.load_class_names(listfile) == R.load_class_names(listfile)
+        cfgf = os.path.join(d, "ape.data")
+        with open(cfgf, "w") as f:
+            f.write("train = a/b.txt\nvalid=c.txt\n\nmesh = m.ply\ngpus = 0,1\n")
+        assert H.read_data_cfg(cfgf) == R.read_data_cfg(cfgf)
+        im = Image.open(bgs[0]).convert("RGB")
+        assert torch.equal(H.image2torch(im), R.image2torch(im))
+        im.save(os.path.join(d, "x.jpg")); im.save(os.path.join(d, "x.gif"))
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for fn in (bgs[0], os.path.join(d, "x.jpg"), os.path.join(d, "x.gif"), cfgf):
+                assert H.get_image_size(fn) == R.get_image_size(fn), fn
+    bb = [[0.1, 0.2, 0.3, 0.4, 9], [0.5, 0.5, 0.1, 0.1, 7]]
+    assert H.scale_bboxes(bb, 640, 480) == R.scale_bboxes(bb, 640, 480)
+    print("host helpers identical to the reference's utils.py functions")
+
+
 AUG_CASES = [  # seed, (ow, oh), (bw, bh), network shape
     (0, (160, 120), (100, 75), (96, 96)),
     (1, (160, 120), (211, 97), (128, 128)),
@@ -352,6 +396,9 @@ if __name__ == "__main__":
     if "--augment-only" in sys.argv:
         main_augment()
         sys.exit(0)
+    if "--helpers-only" in sys.argv:
+        check_host_helpers()
+        sys.exit(0)
     if "--dataset-only" in sys.argv:
         main_dataset()
         sys.exit(0)
@@ -364,3 +411,4 @@ if __name__ == "__main__":
     main_augment()
     main_multires()
     main_dataset()
+    check_host_helpers()
