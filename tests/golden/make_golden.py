@@ -338,7 +338,32 @@ def check_host_helpers():
                 assert H.get_image_size(fn) == R.get_image_size(fn), fn
     bb = [[0.1, 0.2, 0.3, 0.4, 9], [0.5, 0.5, 0.1, 0.1, 7]]
     assert H.scale_bboxes(bb, 640, 480) == R.scale_bboxes(bb, 640, 480)
-    print("host helpers identical to the reference's utils.py functions")
+    # multi-object variants (multi_obj_pose_estimation/utils_multi.py): bbox_iou, nms, read_data_cfg with the 4-GPU default
+    import copy
+    sys.path.insert(0, os.path.join(REF, "multi_obj_pose_estimation"))
+    cwd = os.getcwd()
+    os.chdir(os.path.join(REF, "multi_obj_pose_estimation"))
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import utils_multi as RM
+    finally:
+        os.chdir(cwd)
+    from singleshotpose_b200 import utils_multi as M
+    for _ in range(2000):
+        b1, b2 = list(rng.random(4)), list(rng.random(4))
+        assert M.bbox_iou(b1, b2, False) == RM.bbox_iou(b1, b2, False)
+        c1, c2 = [b1[0], b1[1], b1[0] + b1[2], b1[1] + b1[3]], [b2[0], b2[1], b2[0] + b2[2], b2[1] + b2[3]]
+        assert M.bbox_iou(c1, c2, True) == RM.bbox_iou(c1, c2, True)
+    for _ in range(20):
+        boxes = [list(rng.random(4) * 0.5 + 0.25) + [float(rng.random())] for _ in range(12)]
+        assert M.nms(copy.deepcopy(boxes), 0.3) == RM.nms(copy.deepcopy(boxes), 0.3)
+    with tempfile.TemporaryDirectory() as d:
+        for txt in ("train = a\nvalid = b\n", "gpus = 2\ntrain = a\n"):
+            f = os.path.join(d, "x.data")
+            with open(f, "w") as fh:
+                fh.write(txt)
+            assert M.read_data_cfg(f) == RM.read_data_cfg(f)
+    print("host helpers identical to the reference's utils.py / utils_multi.py functions")
 
 
 AUG_CASES = [  # seed, (ow, oh), (bw, bh), network shape

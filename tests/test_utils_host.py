@@ -95,3 +95,30 @@ def test_dropin_modules_resolve_every_name_the_reference_scripts_use():
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(REPO, "singleshotpose_b200", "dropin"), REPO]))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=str(REPO))
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_multi_object_host_helpers(tmp_path):
+    from singleshotpose_b200 import utils_multi as M
+    assert M.bbox_iou([0.5, 0.5, 0.2, 0.2], [0.5, 0.5, 0.2, 0.2]) == pytest.approx(1.0)
+    assert M.bbox_iou([0.2, 0.2, 0.2, 0.2], [0.8, 0.8, 0.2, 0.2]) == 0.0
+    assert M.bbox_iou([0, 0, 2, 2], [1, 1, 3, 3], x1y1x2y2=True) == pytest.approx(1.0 / 7.0)
+    boxes = [[0.5, 0.5, 0.2, 0.2, 0.9], [0.51, 0.5, 0.2, 0.2, 0.8], [0.1, 0.1, 0.1, 0.1, 0.7], [0.9, 0.9, 0.1, 0.1, 0.0]]
+    kept = M.nms(boxes, 0.4)
+    assert [b[4] for b in kept] == [0.9, 0.7] and boxes[1][4] == 0                 # the suppressed box is zeroed in place
+    assert M.nms([], 0.4) == []
+    f = tmp_path / "m.data"
+    f.write_text("train = a\n")
+    assert M.read_data_cfg(str(f))["gpus"] == "0,1,2,3"
+    f.write_text("gpus = 5\ntrain = a\n")
+    assert M.read_data_cfg(str(f))["gpus"] == "5"
+
+
+def test_dropin_multi_modules_resolve():
+    code = ("from darknet_multi import Darknet\nfrom utils_multi import *\nfrom cfg import parse_cfg\nfrom region_loss_multi import RegionLoss\n"
+            "names = ['get_multi_region_boxes', 'fix_corner_order', 'read_data_cfg', 'logging', 'makedirs', 'get_all_files', 'file_lines', 'pnp',\n"
+            "         'compute_projection', 'calcAngularDistance', 'get_3D_corners', 'get_camera_intrinsic', 'bbox_iou', 'nms', 'convert2cpu']\n"
+            "missing = [n for n in names if n not in globals()]\nassert not missing, missing\nprint('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(REPO, "singleshotpose_b200", "dropin"), REPO]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=str(REPO))
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
