@@ -88,7 +88,7 @@ def test_dropin_modules_resolve_every_name_the_reference_scripts_use():
         "from darknet import Darknet\n"
         "names = ['makedirs', 'get_all_files', 'read_data_cfg', 'file_lines', 'logging', 'get_region_boxes', 'pnp', 'compute_projection',\n"
         "         'compute_transformation', 'calcAngularDistance', 'get_3D_corners', 'get_camera_intrinsic', 'convert2cpu', 'calc_pts_diameter',\n"
-        "         'compute_2d_bb_from_orig_pix', 'fix_corner_order', 'corner_confidence', 'np', 'torch']\n"
+        "         'compute_2d_bb_from_orig_pix', 'fix_corner_order', 'corner_confidence', 'np', 'torch', 'time', 'os', 'math', 'Variable', 'F']\n"
         "missing = [n for n in names if n not in globals()]\n"
         "assert not missing, missing\n"
         "print('ok')\n")
@@ -116,7 +116,8 @@ def test_multi_object_host_helpers(tmp_path):
 def test_dropin_multi_modules_resolve():
     code = ("from darknet_multi import Darknet\nfrom utils_multi import *\nfrom cfg import parse_cfg\nfrom region_loss_multi import RegionLoss\n"
             "names = ['get_multi_region_boxes', 'fix_corner_order', 'read_data_cfg', 'logging', 'makedirs', 'get_all_files', 'file_lines', 'pnp',\n"
-            "         'compute_projection', 'calcAngularDistance', 'get_3D_corners', 'get_camera_intrinsic', 'bbox_iou', 'nms', 'convert2cpu']\n"
+            "         'compute_projection', 'calcAngularDistance', 'get_3D_corners', 'get_camera_intrinsic', 'bbox_iou', 'nms', 'convert2cpu', 'np', 'time',\n"
+            "         'os', 'sys', 'torch', 'calc_pts_diameter']\n"
             "missing = [n for n in names if n not in globals()]\nassert not missing, missing\nprint('ok')\n")
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(REPO, "singleshotpose_b200", "dropin"), REPO]))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=str(REPO))
