@@ -123,3 +123,20 @@ def test_dropin_multi_modules_resolve():
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=str(REPO))
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
 
+
+def test_dropin_wins_over_the_script_directory(tmp_path):
+    """the documented invocation: `python -P script.py` with PYTHONPATH = dropin : repo : checkout.  A fake checkout holds decoy
+    utils.py / darknet.py (the names the drop-in replaces) and dataset.py (a name it does not): with -P the drop-in modules win and
+    dataset.py still comes from the checkout; without -P the script directory shadows the drop-in."""
+    ref = tmp_path / "checkout"
+    ref.mkdir()
+    for name in ("utils", "darknet", "dataset"):
+        (ref / (name + ".py")).write_text("WHO = 'checkout'\n")
+    (ref / "main.py").write_text("import utils, darknet, dataset\nprint(getattr(utils, 'WHO', 'dropin'), getattr(darknet, 'WHO', 'dropin'), dataset.WHO)\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(REPO, "singleshotpose_b200", "dropin"), REPO, str(ref)]))
+    env.pop("PYTHONSAFEPATH", None)
+    safe = subprocess.run([sys.executable, "-P", str(ref / "main.py")], env=env, capture_output=True, text=True)
+    assert safe.returncode == 0 and safe.stdout.split() == ["dropin", "dropin", "checkout"], safe.stderr[-1500:]
+    plain = subprocess.run([sys.executable, str(ref / "main.py")], env=env, capture_output=True, text=True)
+    assert plain.returncode == 0 and plain.stdout.split() == ["checkout", "checkout", "checkout"]
+
