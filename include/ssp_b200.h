@@ -152,6 +152,8 @@ int ssp_project_points(const float* X, int rows, int nv, const double* Rt, const
  *  ssp_aug_resize_u8: Image.crop((x0, y0, x0+in_w, y0+in_h)).resize((out_w, out_h), resample) (image.py:64,69; dataset.py:103);
  *      the crop window may stick out of the source (zero fill), pass (0, 0, src_w, src_h) for a plain resize.
  *  ssp_aug_rgb2hsv_u8 / hsv2rgb_u8: Image.convert('HSV') / ('RGB') (image.py:15,30).
+ *  ssp_aug_to_tensor_u8: torchvision ToTensor (the `transform` of dataset.py:103-118) of a dense uint8 HWC image: float32 CHW,
+ *      byte / 255 as an IEEE division (what the CPU reference computes; a reciprocal multiply differs by 1 ulp).
  *  ssp_aug_sample: change_background (image.py:110-127) -> crop -> resize -> distort_image (image.py:14-32) -> ToTensor
  *      (dataset.py transform) for one sample.  luts = 5 x 256 bytes: posmask, negmask (image.py:121-122), hue, saturation,
  *      value (image.py:17-27) point() tables, built by the host exactly as Image.point() builds them.  Crop window
@@ -162,6 +164,7 @@ int ssp_aug_resize_u8(const void* src, int src_w, int src_h, int x0, int y0, int
                       int out_h, int resample, void* work, long long work_bytes, void* stream);
 int ssp_aug_rgb2hsv_u8(const void* rgb, void* hsv, long long n_pixels, void* stream);
 int ssp_aug_hsv2rgb_u8(const void* hsv, void* rgb, long long n_pixels, void* stream);
+int ssp_aug_to_tensor_u8(const void* hwc_u8, long long n_pixels, float* out_chw, void* stream);
 long long ssp_aug_sample_work_bytes(int ow, int oh, int bw, int bh, int cw, int ch, int out_w, int out_h, int resample);
 int ssp_aug_sample(const void* img, const void* mask, int ow, int oh, const void* bg, int bw, int bh, const void* luts,
                    int pleft, int ptop, int cw, int ch, int out_w, int out_h, int resample, void* work,

@@ -49,6 +49,7 @@ SIGNATURES = {
     "ssp_aug_resize_u8": [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p, _ll, _p],
     "ssp_aug_rgb2hsv_u8": [_p, _p, _ll, _p],
     "ssp_aug_hsv2rgb_u8": [_p, _p, _ll, _p],
+    "ssp_aug_to_tensor_u8": [_p, _ll, _p, _p],
     "ssp_aug_sample_work_bytes": [_i, _i, _i, _i, _i, _i, _i, _i, _i],
     "ssp_aug_sample": [_p, _p, _i, _i, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _p, _p],
 }

@@ -105,7 +105,8 @@ def print_cfg(blocks):
 
 def _take(buf, start, tensor):
     n = tensor.numel()
-    tensor.data.copy_(torch.from_numpy(np.ascontiguousarray(buf[start:start + n])).view(tensor.shape))
+    with torch.no_grad():          # a tracked in-place write: bumps tensor._version, which the engine's operand-plane cache keys on
+        tensor.copy_(torch.from_numpy(np.ascontiguousarray(buf[start:start + n])).view(tensor.shape))
     return start + n
 
 

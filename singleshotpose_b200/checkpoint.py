@@ -17,10 +17,9 @@ def save_checkpoint(model, optimizer, weightfile):
     """model.save_weights(weightfile) + `<weightfile>.optim.pt` (optimiser state_dict, model.seen, model.iter)."""
     model.save_weights(weightfile)
     sd = optimizer.state_dict()
-    for ent in sd.get("state", {}).values():
-        for k, v in ent.items():
-            if torch.is_tensor(v):
-                ent[k] = v.detach().cpu()
+    # torch.optim.SGD.state_dict() hands out the LIVE per-parameter dicts: build new ones instead of moving its buffers to the CPU
+    state = {i: {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in ent.items()} for i, ent in sd.get("state", {}).items()}
+    sd = {"state": state, "param_groups": sd["param_groups"]}
     tmp = weightfile + _SUFFIX + ".tmp"
     torch.save({"optimizer": sd, "seen": int(model.seen), "iter": int(getattr(model, "iter", 0))}, tmp)
     os.replace(tmp, weightfile + _SUFFIX)           # atomic: a crash mid-save never leaves a truncated state file

@@ -61,6 +61,16 @@ __global__ void aug_distort_kernel(const uint8_t* __restrict__ src, long long n_
   }
 }
 
+// torchvision ToTensor of a dense uint8 HWC RGB image: float32 CHW planes, byte / 255 as an IEEE division (dataset.py:103-118 transform)
+__global__ void aug_to_tensor_kernel(const uint8_t* __restrict__ src, long long n_px, float* __restrict__ out_chw) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
+    const uint8_t* s = src + 3 * i;
+    out_chw[i] = (float)s[0] / 255.0f;
+    out_chw[n_px + i] = (float)s[1] / 255.0f;
+    out_chw[2 * n_px + i] = (float)s[2] / 255.0f;
+  }
+}
+
 namespace {
 inline int blocks_for(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
@@ -120,6 +130,14 @@ int aug_convert_u8(const uint8_t* src, uint8_t* dst, long long n_px, int mode, c
   if (!src || !dst || n_px < 0 || (mode != 1 && mode != 2)) return fail_msg(SSP_ERR_ARG, "ssp_aug_rgb2hsv_u8/hsv2rgb_u8: bad argument");
   if (n_px == 0) return SSP_OK;
   aug_distort_kernel<<<blocks_for(n_px, 256), 256, 0, s>>>(src, n_px, nullptr, mode, dst, nullptr);
+  SSP_CHECK_LAUNCH();
+  return SSP_OK;
+}
+
+int aug_to_tensor_u8(const uint8_t* src, long long n_px, float* out_chw, cudaStream_t s) {
+  if (!src || !out_chw || n_px < 0) return fail_msg(SSP_ERR_ARG, "ssp_aug_to_tensor_u8: bad argument");
+  if (n_px == 0) return SSP_OK;
+  aug_to_tensor_kernel<<<blocks_for(n_px, 256), 256, 0, s>>>(src, n_px, out_chw);
   SSP_CHECK_LAUNCH();
   return SSP_OK;
 }

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) region_decode_kernel(const float* __restr
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const int i = si[0], cy = i / W, cx = i % W;
+    const int i = si[0] == 0x7fffffff ? 0 : si[0], cy = i / W, cx = i % W;     // every confidence NaN: decode cell 0 instead of reading out of bounds
     float* bx = boxes + (long long)b * (2 * K + 3);
     for (int k = 0; k < K; k++) {
       float vx = o[(2 * k) * HW + i], vy = o[(2 * k + 1) * HW + i];

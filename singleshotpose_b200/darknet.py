@@ -173,6 +173,7 @@ class Darknet(nn.Module):
                     start = load_conv_bn(buf, start, model[0], model[1])
                 else:
                     start = load_conv(buf, start, model[0])
+        self._engine.invalidate_packed_weights()      # the fp16 operand copies of the conv weights are stale now
         return start
 
     def load_weights(self, weightfile):

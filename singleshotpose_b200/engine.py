@@ -131,7 +131,13 @@ class Buffers:
         f16 = torch.float16
         self.x_hi, self.x_lo, self.y, self.rows = [], [], [], []
         self.dy, self.dx = [], []
+        # per-layer BN state (batch sums, mean / invstd, folded scale / shift, backward sums) lives with the activations it
+        # describes: a forward of another shape or mode between a training forward and its backward cannot overwrite it
+        self.stat = []
         for L in eng.layers:
+            st = {k: torch.zeros(L.cout, dtype=torch.float64, device=dev) for k in ("ssum", "ssq", "s1", "s2")}
+            st.update({k: torch.zeros(L.cout, dtype=torch.float32, device=dev) for k in ("mean", "invstd", "scale", "shift")})
+            self.stat.append(st)
             # spatial size of this layer for the actual input resolution
             h, w = eng.spatial(L, H, W)
             rows = _lib.flat_alloc_rows(N, h, w)
@@ -242,25 +248,24 @@ class Engine:
         self._weights_version = None
 
     def _alloc_layer_state(self, dev):
-        self.w_hi, self.w_lo, self.w_d, self.stat = [], [], [], []
+        self.w_hi, self.w_lo, self.w_d = [], [], []
         f16 = torch.float16
         for L in self.layers:
             kf = _rup(L.k_taps * L.k_cin if not L.first else 32, 8)
             self.w_hi.append(torch.zeros(L.cout, kf, dtype=f16, device=dev))
             self.w_lo.append(torch.zeros(L.cout, kf, dtype=f16, device=dev))
             self.w_d.append(None if L.first else torch.zeros(L.cin, _rup(L.taps * L.cout, 8), dtype=self.grad_dtype, device=dev))
-            st = {}
-            for k in ("ssum", "ssq", "s1", "s2"):
-                st[k] = torch.zeros(L.cout, dtype=torch.float64, device=dev)
-            for k in ("mean", "invstd", "scale", "shift"):
-                st[k] = torch.zeros(L.cout, dtype=torch.float32, device=dev)
-            self.stat.append(st)
 
     def grad_view(self, p):
         return self._slices[id(p)][2]
 
     def _params_version(self):
         return tuple(p._version for p in self.model.parameters())
+
+    def invalidate_packed_weights(self):
+        """the fp32 master weights changed behind the version counters (load_weights, a graph replay, an external optimiser
+        writing through .data): the next forward re-packs W_hi / W_lo / W_d"""
+        self._weights_version = None
 
     def pack_weights(self, force=False):
         ver = self._params_version()
@@ -337,7 +342,7 @@ class Engine:
             i = L.index
             conv, bn = mods[i]
             h, w = self.spatial(L, H, W)
-            st = self.stat[i]
+            st = B.stat[i]
             a_lo = None if self.fast else ptr(B.x_lo[i])
             b_lo = None if self.fast else ptr(self.w_lo[i])
             xin = B.x_hi[i]
@@ -413,7 +418,7 @@ class Engine:
             i = L.index
             conv, bn = mods[i]
             h, w = self.spatial(L, H, W)
-            st = self.stat[i]
+            st = B.stat[i]
             dy = B.dy[i]
             if L.bn:
                 srcs = []
@@ -444,7 +449,7 @@ class Engine:
                 prod = self._direct_producer.get(i) if self.fuse_bnbwd and self._conv_impl(L.cin, L.taps) == _lib.IMPL_TC2 else None
                 if prod is not None:
                     j, c0 = prod
-                    Lj, stj = self.layers[j], self.stat[j]
+                    Lj, stj = self.layers[j], B.stat[j]
                     self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm_dgrad_bnred", ptr(dy), B.rows[i], dy.shape[1], L.cout, ptr(wd), L.cin, wd.shape[1],
                                self.grad_fmt, N, h, w, L.taps, L.cin, ptr(B.dx[i]), B.dx[i].shape[1], B.rows[i], ptr(B.y[j]), B.y[j].shape[1],
                                ptr(stj["scale"]), ptr(stj["shift"]), ptr(stj["mean"]), ptr(stj["invstd"]), Lj.slope, c0, c0 + Lj.cout,

@@ -17,6 +17,22 @@ class GraphedTrainStep:
         self.graph = None
         self.loss = None
         self._warmup = warmup
+        self._captured = None
+
+    def _hyper(self):
+        """everything the captured launches carry BY VALUE: lr / momentum / weight decay (kernel scalars of ssp_sgd_step_flat) and
+        the confidence-loss gate epoch > pretrain_num_epochs (region_loss.py:156).  adjust_learning_rate (train.py:34-46) rewrites
+        param_groups every batch and the gate flips once per run: a replay with stale values would silently train wrong."""
+        g = self.optimizer.param_groups[0]
+        gate = self.epoch > getattr(self.criterion, "pretrain_num_epochs", -1)
+        return (float(g["lr"]), float(g.get("momentum", 0.0)), float(g.get("weight_decay", 0.0)), bool(gate))
+
+    def set_epoch(self, epoch):
+        self.epoch = epoch
+
+    def _ensure_current(self):
+        if self.graph is None or self._captured != self._hyper():
+            self.capture(warmup=0 if self.graph is not None else None)
 
     def _step(self):
         self.optimizer.zero_grad()
@@ -28,22 +44,24 @@ class GraphedTrainStep:
         self.optimizer.step()
         return loss
 
-    def capture(self):
+    def capture(self, warmup=None):
         verbose, self.criterion.verbose = getattr(self.criterion, "verbose", False), False
         eng = self.model._engine
         prof, eng.profile = eng.profile, None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(self._warmup):          # allocations, cudaFuncSetAttribute, optimizer state: all before capture
+            for _ in range(self._warmup if warmup is None else warmup):          # allocations, cudaFuncSetAttribute, optimizer state: all before capture
                 self._step()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad()
+        eng.invalidate_packed_weights()            # the weight re-pack must be part of the captured step
         with torch.cuda.graph(g):
             self.loss = self._step()
         self.graph = g
+        self._captured = self._hyper()
         self.criterion.verbose = verbose
         eng.profile = prof
         return self
@@ -64,17 +82,21 @@ class GraphedTrainStep:
 
     def run_staged(self):
         """replay on the batch passed to the last stage() call"""
+        self._ensure_current()
         cur = torch.cuda.current_stream()
         cur.wait_event(self._staged)
         self.x.copy_(self._x_stage, non_blocking=True)          # device-to-device, ~0.1 ms
         self.t.copy_(self._t_stage, non_blocking=True)
         self._consumed.record()
         self.graph.replay()
+        self.model._engine.invalidate_packed_weights()     # the replayed SGD moved the master weights past the packed copies
         return self.loss
 
     def __call__(self, x, target):
         """x, target: host (pinned) or device tensors of the captured shapes -> loss tensor (device, 0-dim)."""
+        self._ensure_current()
         self.x.copy_(x, non_blocking=True)
         self.t.copy_(target, non_blocking=True)
         self.graph.replay()
+        self.model._engine.invalidate_packed_weights()
         return self.loss

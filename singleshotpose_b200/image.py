@@ -164,14 +164,25 @@ def hsv2rgb_u8(hsv):
     return out
 
 
-def _validation_batch(imgs, shape, dev, resample, resize_fn):
+def to_tensor_u8(img, out=None):
+    """torchvision ToTensor of a uint8 HxWx3 CUDA image -> float32 (3,H,W) in [0,1] (byte / 255 as an IEEE division, in-kernel)."""
+    _require_cuda(img, "to_tensor_u8")
+    img = _u8_hwc(img, "img")
+    h, w = img.shape[:2]
+    if out is None:
+        out = torch.empty(3, h, w, dtype=torch.float32, device=img.device)
+    call("ssp_aug_to_tensor_u8", ptr(img), h * w, ptr(out), stream_ptr())
+    return out
+
+
+def _validation_batch(imgs, shape, dev, resample, resize_fn, to_tensor_fn):
     W, H = int(shape[0]), int(shape[1])
     out = torch.empty(len(imgs), 3, H, W, dtype=torch.float32, device=dev)
     for i, a in enumerate(imgs):
         a = _u8_hwc(a, "img")
         d = a.to(dev, non_blocking=True) if torch.is_tensor(a) else torch.from_numpy(a).to(dev, non_blocking=True)
         r = resize_fn(d, (W, H), resample)                    # (H, W, 3) uint8, byte-identical to PIL
-        out[i] = r.permute(2, 0, 1).to(torch.float32).div_(255)      # torchvision ToTensor
+        to_tensor_fn(r, out[i])                               # torchvision ToTensor
     return out
 
 
@@ -182,7 +193,7 @@ def load_validation_batch(imgs, shape, device, resample=BICUBIC):
     dev = torch.device(device)
     if dev.type != "cuda":
         raise SspError("load_validation_batch needs a CUDA device (no CPU fallback); got %s" % dev)
-    return _validation_batch(imgs, shape, dev, resample, resize_u8)
+    return _validation_batch(imgs, shape, dev, resample, resize_u8, to_tensor_u8)
 
 
 def _a16(n):

@@ -61,8 +61,10 @@ class RegionLoss(nn.Module):
         if self.num_anchors != 1:
             raise NotImplementedError("multi-anchor RegionLoss (region_loss_multi.py) is not built yet")
         nl = 2 * self.num_keypoints + 3
-        if target.dim() != 2 or target.size(1) < nl or target.size(0) != output.size(0):
-            raise ValueError("target must be (batch, 50*%d)" % nl)
+        if target.dim() != 2 or target.size(1) != 50 * nl or target.size(0) != output.size(0):
+            # the kernel strides rows by 50*nl and reads the first ground truth (the reference supports exactly one per image:
+            # a second one is a broadcast error at region_loss.py:39, none an IndexError at :40 -- SURVEY 8a/a10)
+            raise ValueError("target must be (batch, 50*%d), got %s" % (nl, tuple(target.shape)))
         tgt = target.detach().to(device=output.device, dtype=torch.float32, non_blocking=True).contiguous()
         loss = _RegionLossFn.apply(output, tgt, self, epoch)
         if self.verbose:

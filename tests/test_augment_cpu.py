@@ -205,14 +205,15 @@ def test_staging_layout_feeds_the_kernel_core(host):
 
 
 def test_validation_batch_glue_with_oracle_resize():
-    """load_validation_batch = per-image resize_u8 + ToTensor; with the resize swapped for the oracle (the GPU kernel itself is
+    """load_validation_batch = per-image resize_u8 + to_tensor_u8; with both kernels swapped for the oracle (the GPU kernel itself is
     tested in test_gpu_augment.py) the stacking / dtype / layout glue is checked on the CPU"""
     import torch
     from singleshotpose_b200._lib import SspError
     rng = np.random.default_rng(3)
     imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in ((48, 64), (30, 30), (64, 48))]
     oracle_resize = lambda t, size, resample: torch.from_numpy(A.resize_u8(t.numpy(), size, resample))
-    x = I._validation_batch(imgs, (32, 24), torch.device("cpu"), I.BICUBIC, oracle_resize)
+    oracle_to_tensor = lambda r, out: out.copy_(r.permute(2, 0, 1).float().div(255))
+    x = I._validation_batch(imgs, (32, 24), torch.device("cpu"), I.BICUBIC, oracle_resize, oracle_to_tensor)
     assert x.shape == (3, 3, 24, 32) and x.dtype == torch.float32
     for i, im in enumerate(imgs):
         assert torch.equal(x[i], torch.from_numpy(A.resize_u8(im, (32, 24))).permute(2, 0, 1).float().div(255))
