@@ -114,6 +114,23 @@ int ssp_pack_weights_v2(const float* w, int cout, int taps, int cin, void* fwd_h
                         void* dgrad, int dgrad_ld, int dgrad_fmt, void* stream);
 int ssp_sgd_step_flat(float* p, const float* g, float* v, long long n, float lr, float momentum,
                       float weight_decay, float grad_scale, void* stream);
+/* SGD and the operand-plane re-pack in ONE pass over the flat buffers (csrc/sgd_pack.cu).  `segments` is a DEVICE array with one
+ * entry per parameter tensor in flat-buffer order; taps == 0 marks a tensor without operand planes (BN affine, bias).  A conv
+ * weight [cout][taps][cin] owns ssp_sgd_segment_blocks() consecutive blocks starting at block0 (prefix sum, filled by the
+ * caller); a launch covers blocks [block_begin, block_end), i.e. any run of whole segments: the data-parallel path updates one
+ * gradient bucket at a time.  Writes p, v and -- where the pointers are non-null -- W_hi / W_lo [cout][ld_f] (k = tap*cin + ci)
+ * and W_d [cin][ld_d] (k = (taps-1-tap)*cout + co), exactly the bytes ssp_pack_weights would produce from the updated p. */
+typedef struct ssp_sgd_segment {
+  long long off, n;                 /* element offset and count inside the flat buffers */
+  int cout, taps, cin;              /* conv weight geometry; taps == 0: plain tensor */
+  int ld_f, ld_d, d_fmt;            /* row pitches (elements) of the planes; SSP_FMT_* of W_d */
+  void* f_hi; void* f_lo; void* d;  /* device planes, each may be NULL */
+  int block0, reserved;
+} ssp_sgd_segment;
+int ssp_sgd_segment_blocks(int cout, int taps, int cin, long long n);
+int ssp_sgd_pack_step(const ssp_sgd_segment* segments_dev, int n_segments, int block_begin, int block_end, float* p,
+                      const float* g, float* v, float lr, float momentum, float weight_decay, float grad_scale,
+                      void* stream);
 
 /* ---- RegionLoss.forward + build_targets + gradient (region_loss.py:9-175); acc = 8 doubles:
  *      loss_x, loss_y, loss_conf, nGT, nCorrect, nProposals ---- */

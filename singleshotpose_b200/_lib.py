@@ -39,6 +39,8 @@ SIGNATURES = {
     "ssp_pack_weights": [_p, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p],
     "ssp_pack_weights_v2": [_p, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p],
     "ssp_sgd_step_flat": [_p, _p, _p, _ll, _f, _f, _f, _f, _p],
+    "ssp_sgd_segment_blocks": [_i, _i, _i, _ll],
+    "ssp_sgd_pack_step": [_p, _i, _i, _i, _p, _p, _p, _f, _f, _f, _f, _p],
     "ssp_region_loss_fwd_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _f, _p],
     "ssp_region_decode_argmax": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p],
     "ssp_region_loss_multi_fwd_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _f, _f, _f, _f, _f, _i, _f, _p],

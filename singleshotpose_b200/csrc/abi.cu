@@ -40,6 +40,7 @@ int bias_grad_nchw(const float*, float*, int, int, int, int, float, cudaStream_t
 int pack_weights(const float*, int, int, int, void*, void*, int, void*, int, int, cudaStream_t);
 int pack_weights_v2(const float*, int, int, int, void*, void*, int, void*, int, int, cudaStream_t);
 int sgd_step_flat(float*, const float*, float*, long long, float, float, float, float, cudaStream_t);
+int sgd_pack_step(const ssp_sgd_segment*, int, int, int, float*, const float*, float*, float, float, float, float, cudaStream_t);
 int region_loss_fwd_bwd(const float*, const float*, float*, double*, int, int, int, int, int, float, float, float, float, int, float, cudaStream_t);
 int region_decode_argmax(const float*, int, int, int, int, int, int, float*, float*, float*, cudaStream_t);
 int region_loss_multi_fwd_bwd(const float*, const float*, float*, double*, int, int, int, int, int, int, const float*, int, float, float, float,
@@ -143,6 +144,14 @@ int ssp_pack_weights_v2(const float* w, int cout, int taps, int cin, void* f_hi,
 }
 int ssp_pack_weights(const float* w, int cout, int taps, int cin, void* f_hi, void* f_lo, int ld_f, void* d, int ld_d, int d_fmt, void* s) {
   return pack_weights(w, cout, taps, cin, f_hi, f_lo, ld_f, d, ld_d, d_fmt, ST(s));
+}
+int ssp_sgd_segment_blocks(int cout, int taps, int cin, long long n) {
+  if (taps == 0) return (int)((n + 1023) / 1024);
+  return ((cin + 63) / 64) * ((cout + 63) / 64) * taps;
+}
+int ssp_sgd_pack_step(const ssp_sgd_segment* segs, int n_seg, int b0, int b1, float* p, const float* g, float* v, float lr, float mu, float wd,
+                      float gscale, void* s) {
+  return sgd_pack_step(segs, n_seg, b0, b1, p, g, v, lr, mu, wd, gscale, ST(s));
 }
 int ssp_sgd_step_flat(float* p, const float* g, float* v, long long n, float lr, float mu, float wd, float gscale, void* s) { return sgd_step_flat(p, g, v, n, lr, mu, wd, gscale, ST(s)); }
 int ssp_region_loss_fwd_bwd(const float* out, const float* target, float* grad, double* acc, int B, int K, int nC, int H, int W, float coord_scale,

@@ -495,15 +495,15 @@ __global__ void sgd_flat_kernel(float* __restrict__ p, const float* __restrict__
     float4 pp = *reinterpret_cast<float4*>(p + i4);
     const float4 gg = *reinterpret_cast<const float4*>(g + i4);
     float4 vv = *reinterpret_cast<float4*>(v + i4);
-    vv.x = mu * vv.x + (gg.x * gscale + wd * pp.x); vv.y = mu * vv.y + (gg.y * gscale + wd * pp.y);
-    vv.z = mu * vv.z + (gg.z * gscale + wd * pp.z); vv.w = mu * vv.w + (gg.w * gscale + wd * pp.w);
-    pp.x -= lr * vv.x; pp.y -= lr * vv.y; pp.z -= lr * vv.z; pp.w -= lr * vv.w;
+    sgd_update(pp.x, gg.x, vv.x, lr, mu, wd, gscale); sgd_update(pp.y, gg.y, vv.y, lr, mu, wd, gscale);
+    sgd_update(pp.z, gg.z, vv.z, lr, mu, wd, gscale); sgd_update(pp.w, gg.w, vv.w, lr, mu, wd, gscale);
     *reinterpret_cast<float4*>(v + i4) = vv;
     *reinterpret_cast<float4*>(p + i4) = pp;
   } else {
     for (long long i = i4; i < n; i++) {
-      const float vn = mu * v[i] + (g[i] * gscale + wd * p[i]);
-      v[i] = vn; p[i] -= lr * vn;
+      float pv = p[i], vv = v[i];
+      sgd_update(pv, g[i], vv, lr, mu, wd, gscale);
+      v[i] = vv; p[i] = pv;
     }
   }
 }

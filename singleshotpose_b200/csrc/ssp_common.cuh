@@ -195,6 +195,14 @@ __host__ __device__ inline uint32_t umma_idesc_f16(int a_fmt, int b_fmt, int a_m
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// optim.SGD(momentum, dampening = 0, weight_decay), train.py:388:  g += wd*p ; v = mu*v + g ; p -= lr*v  (torch's first step,
+// v = g, is the same with v0 = 0).  Explicit FMAs: every kernel that applies the update produces the same bits.
+__device__ __forceinline__ void sgd_update(float& p, float g, float& v, float lr, float mu, float wd, float gscale) {
+  const float vn = fmaf(mu, v, fmaf(wd, p, g * gscale));
+  v = vn;
+  p = fmaf(-lr, vn, p);
+}
+
 // Sum over the 32 lanes of v[j], delivered to lane j (31 shuffles instead of 32*5).
 __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
 #pragma unroll

@@ -189,6 +189,7 @@ class Engine:
             if Lp.bn and len(Lp.dests) == 1 and Lp.dests[0][2] == _lib.ROUTE_DIRECT and Lp.cout % 32 == 0 and Lp.cout <= 1024 and Lp.dests[0][1] % 32 == 0:
                 self._direct_producer.setdefault(Lp.dests[0][0], (Lp.index, Lp.dests[0][1]))
         self._side = None
+        self.grad_ready_hook = None  # fn(first layer index, stream): every gradient of layers >= that index is complete in `stream` order
         self.profile = None          # set to [] to record (kind, layer block, algorithmic flops, start event, end event) per GEMM launch
         net = model.blocks[0]
         self.base_hw = (int(net["height"]), int(net["width"]))
@@ -246,6 +247,7 @@ class Engine:
         self._alloc_layer_state(device)
         self._buffers = {}
         self._weights_version = None
+        self._seg_table = None
 
     def _alloc_layer_state(self, dev):
         self.w_hi, self.w_lo, self.w_d = [], [], []
@@ -255,6 +257,70 @@ class Engine:
             self.w_hi.append(torch.zeros(L.cout, kf, dtype=f16, device=dev))
             self.w_lo.append(torch.zeros(L.cout, kf, dtype=f16, device=dev))
             self.w_d.append(None if L.first else torch.zeros(L.cin, _rup(L.taps * L.cout, 8), dtype=self.grad_dtype, device=dev))
+
+    # ------------------------------------------------------------------ fused SGD + re-pack work list, gradient buckets
+    _SEG_DTYPE = [("off", "<i8"), ("n", "<i8"), ("cout", "<i4"), ("taps", "<i4"), ("cin", "<i4"), ("ld_f", "<i4"), ("ld_d", "<i4"),
+                  ("d_fmt", "<i4"), ("f_hi", "<u8"), ("f_lo", "<u8"), ("d", "<u8"), ("block0", "<i4"), ("reserved", "<i4")]
+
+    def sgd_segments(self):
+        """device table (ssp_sgd_segment, include/ssp_b200.h) for ssp_sgd_pack_step: one entry per parameter tensor in flat order.
+        Returns (table tensor, [(block0, nblocks)] per parameter)."""
+        if getattr(self, "_seg_table", None) is not None:
+            return self._seg_table, self._seg_blocks
+        import numpy as np
+        lib = _lib.load()
+        conv_of = {id(conv.weight): L for L, (conv, _) in zip(self.layers, self.conv_modules())}
+        params = list(self.model.parameters())
+        tab = np.zeros(len(params), dtype=np.dtype(self._SEG_DTYPE))
+        assert tab.dtype.itemsize == 72
+        blocks, b0 = [], 0
+        for k, p in enumerate(params):
+            off, n, _g = self._slices[id(p)]
+            e = tab[k]
+            e["off"], e["n"], e["block0"] = off, n, b0
+            L = conv_of.get(id(p))
+            if L is not None:
+                i = L.index
+                if L.first:        # [32][9][3] -> K = 27: a 1-tap GEMM over the im2col'ed input, no data gradient
+                    e["cout"], e["taps"], e["cin"] = L.cout, 1, 27
+                else:
+                    e["cout"], e["taps"], e["cin"] = L.cout, L.taps, L.cin
+                    e["d"], e["ld_d"], e["d_fmt"] = self.w_d[i].data_ptr(), self.w_d[i].shape[1], self.grad_fmt
+                e["f_hi"], e["f_lo"], e["ld_f"] = self.w_hi[i].data_ptr(), self.w_lo[i].data_ptr(), self.w_hi[i].shape[1]
+            nb = int(lib.ssp_sgd_segment_blocks(int(e["cout"]), int(e["taps"]), int(e["cin"]), n))
+            blocks.append((b0, nb))
+            b0 += nb
+        self._seg_table = torch.from_numpy(tab.view(np.uint8).reshape(-1).copy()).to(self.device)
+        self._seg_blocks = blocks
+        return self._seg_table, blocks
+
+    def grad_buckets(self, n_buckets=4):
+        """contiguous runs of layers, LAST layers first (the order in which backward completes their gradients), each about
+        1/n_buckets of the parameters: [(first layer index, (elem lo, elem hi), (block lo, block hi))].  SURVEY 8e: 'bucket in
+        reverse layer order to overlap with backward'."""
+        _tab, blocks = self.sgd_segments()
+        params = list(self.model.parameters())
+        index_of = {id(p): k for k, p in enumerate(params)}
+        per_layer = []                     # (layer index, first param k, last param k)
+        for L, (conv, bn) in zip(self.layers, self.conv_modules()):
+            ks = [index_of[id(q)] for q in ([conv.weight] + ([bn.weight, bn.bias] if bn is not None else [conv.bias]))]
+            per_layer.append((L.index, min(ks), max(ks)))
+        total = self.flat_params.numel()
+        target = 0.9 * total / max(1, n_buckets)
+        out, acc, hi_k = [], 0, None
+        for (li, k0, k1) in reversed(per_layer):
+            hi_k = k1 if hi_k is None else hi_k
+            acc += sum(self._slices[id(params[k])][1] for k in range(k0, k1 + 1))
+            if acc >= target and len(out) < n_buckets - 1 and li > 0:
+                out.append((li, k0, hi_k)); acc, hi_k = 0, None
+        if hi_k is not None:
+            out.append((0, 0, hi_k))
+        res = []
+        for (li, k0, k1) in out:
+            e0 = self._slices[id(params[k0])][0]
+            e1 = self._slices[id(params[k1])][0] + self._slices[id(params[k1])][1]
+            res.append((li, (e0, e1), (blocks[k0][0], blocks[k1][0] + blocks[k1][1])))
+        return res
 
     def grad_view(self, p):
         return self._slices[id(p)][2]
@@ -467,5 +533,9 @@ class Engine:
             else:
                 self._gemm("wgrad", L, N, h, w, "ssp_wgrad_gemm", self.wgrad_impl, ptr(dy), B.rows[i], dy.shape[1], L.cout, self.grad_fmt,
                            ptr(xh), B.rows[i], xh.shape[1], L.cin, self.grad_fmt, N, h, w, L.taps, ptr(dw), L.cin, L.cin, inv, ws, stream=wstream)
+            if self.grad_ready_hook is not None:
+                # the weight-gradient stream has waited for this layer's dY event, i.e. for every main-stream gradient write
+                # (dgamma / dbeta / dbias) of the layers >= i as well
+                self.grad_ready_hook(i, side if overlap else main)
         if overlap:
             main.wait_stream(side)

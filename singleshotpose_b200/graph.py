@@ -33,6 +33,14 @@ class GraphedTrainStep:
     def _ensure_current(self):
         if self.graph is None or self._captured != self._hyper():
             self.capture(warmup=0 if self.graph is not None else None)
+        eng = self.model._engine
+        if getattr(self.optimizer, "fused", False):
+            eng.pack_weights()      # no-op unless the weights changed outside the graph (load_weights, load_state_dict): the
+                                    # captured step has no re-pack of its own, FlatSGD rewrites the operand planes as it updates
+
+    def _after_replay(self):
+        if not getattr(self.optimizer, "fused", False):
+            self.model._engine.invalidate_packed_weights()     # the replayed SGD moved the master weights past the packed copies
 
     def _step(self):
         self.optimizer.zero_grad()
@@ -57,7 +65,10 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad()
-        eng.invalidate_packed_weights()            # the weight re-pack must be part of the captured step
+        if getattr(self.optimizer, "fused", False):
+            eng.pack_weights()                     # FlatSGD rewrites the operand planes itself: start the graph from current ones
+        else:
+            eng.invalidate_packed_weights()        # the weight re-pack must be part of the captured step
         with torch.cuda.graph(g):
             self.loss = self._step()
         self.graph = g
@@ -89,7 +100,7 @@ class GraphedTrainStep:
         self.t.copy_(self._t_stage, non_blocking=True)
         self._consumed.record()
         self.graph.replay()
-        self.model._engine.invalidate_packed_weights()     # the replayed SGD moved the master weights past the packed copies
+        self._after_replay()
         return self.loss
 
     def __call__(self, x, target):
@@ -98,5 +109,5 @@ class GraphedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.t.copy_(target, non_blocking=True)
         self.graph.replay()
-        self.model._engine.invalidate_packed_weights()
+        self._after_replay()
         return self.loss

@@ -277,6 +277,70 @@ def test_sgd_flat_matches_torch_sgd():
     assert torch.allclose(p.cpu(), p_t.detach(), rtol=1e-5, atol=1e-6)
 
 
+def _seg_table(entries):
+    """entries: dicts of ssp_sgd_segment fields -> (device table, total blocks)"""
+    import numpy as np
+    from singleshotpose_b200.engine import Engine
+    tab = np.zeros(len(entries), dtype=np.dtype(Engine._SEG_DTYPE))
+    b0 = 0
+    for e, d in zip(tab, entries):
+        for k, v in d.items():
+            e[k] = v
+        e["block0"] = b0
+        b0 += int(_lib.load().ssp_sgd_segment_blocks(int(e["cout"]), int(e["taps"]), int(e["cin"]), int(e["n"])))
+    return torch.from_numpy(tab.view(np.uint8).reshape(-1).copy()).to(DEV), b0
+
+
+def test_sgd_pack_step_matches_separate_kernels():
+    """the fused optimiser + re-pack pass (csrc/sgd_pack.cu) writes exactly the bytes of ssp_sgd_step_flat followed by
+    ssp_pack_weights: parameters, momentum, forward hi/lo planes and the transposed data-gradient plane; launched bucket by
+    bucket (block sub-ranges) it gives the same result as in one launch"""
+    shapes = [(32, 1, 27), (64, 9, 32), (130, 9, 70), (0, 0, 0, 70), (0, 0, 0, 5000), (20, 1, 1024), (256, 9, 128)]   # 4-tuples: plain tensors
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    sizes = [(s[0] * s[1] * s[2]) if len(s) == 3 else s[3] for s in shapes]
+    total = sum(sizes)
+    p0 = torch.randn(total, device=DEV, generator=gen); g = torch.randn(total, device=DEV, generator=gen); v0 = torch.randn(total, device=DEV, generator=gen)
+    hyper = (0.01, 0.9, 0.032, 0.5)
+    # separate kernels
+    p_ref, v_ref = p0.clone(), v0.clone()
+    call("ssp_sgd_step_flat", ptr(p_ref), ptr(g), ptr(v_ref), total, *hyper, stream_ptr())
+    planes_ref, planes, entries, off = [], [], [], 0
+    for s, n in zip(shapes, sizes):
+        if len(s) == 4:
+            entries.append(dict(off=off, n=n)); planes_ref.append(None); planes.append(None)
+        else:
+            cout, taps, cin = s
+            ld_f, ld_d = (taps * cin + 7) // 8 * 8, (taps * cout + 7) // 8 * 8
+            mk = lambda: (torch.zeros(cout, ld_f, dtype=torch.float16, device=DEV), torch.zeros(cout, ld_f, dtype=torch.float16, device=DEV),
+                          torch.zeros(cin, ld_d, dtype=torch.float16, device=DEV) if taps * cin != 27 else None)
+            a, b = mk(), mk()
+            call("ssp_pack_weights", ptr(p_ref[off:off + n]), cout, taps, cin, ptr(a[0]), ptr(a[1]), ld_f, ptr(a[2]), ld_d if a[2] is not None else 0, _lib.FMT_F16, stream_ptr())
+            planes_ref.append(a); planes.append(b)
+            entries.append(dict(off=off, n=n, cout=cout, taps=taps, cin=cin, ld_f=ld_f, ld_d=ld_d if b[2] is not None else 0, d_fmt=_lib.FMT_F16,
+                                f_hi=b[0].data_ptr(), f_lo=b[1].data_ptr(), d=b[2].data_ptr() if b[2] is not None else 0))
+        off += n
+    table, nblocks = _seg_table(entries)
+    for cuts in ([0, nblocks], None):
+        if cuts is None:                 # bucket by bucket, last segments first (the data-parallel order)
+            b0s = [int(x) for x in table.cpu().view(torch.int32).view(len(entries), 18)[:, 16]] + [nblocks]
+            cuts = [b0s[0], b0s[3], b0s[5], nblocks]
+        p, v = p0.clone(), v0.clone()
+        for pl in planes:
+            if pl is not None:
+                for t in pl:
+                    if t is not None:
+                        t.zero_()
+        for lo, hi in reversed(list(zip(cuts[:-1], cuts[1:]))):
+            call("ssp_sgd_pack_step", ptr(table), len(entries), lo, hi, ptr(p), ptr(g), ptr(v), *hyper, stream_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(p, p_ref) and torch.equal(v, v_ref)
+        for a, b in zip(planes_ref, planes):
+            if a is not None:
+                for x, y in zip(a, b):
+                    if x is not None:
+                        assert torch.equal(x.view(torch.int16), y.view(torch.int16))
+
+
 def test_library_reports_errors():
     with pytest.raises(_lib.SspError):
         call("ssp_pnp_batched", None, 1, None, None, 9, 1, 20, None, None, None, stream_ptr())

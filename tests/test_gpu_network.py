@@ -237,3 +237,59 @@ def test_graphed_train_step_matches_eager(cfg_path):
         if it == 0:      # identical after the first step; later steps diverge chaotically from 1e-7 differences (see profiles/r01_grad_noise_floor.txt)
             for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
                 assert _rel(p.detach().cpu(), q.detach().cpu()) < 1e-5, n
+
+
+def test_load_weights_after_forward_refreshes_operand_planes(cfg_path, tmp_path):
+    """load_weights() after a forward pass must not leave the packed fp16 conv operands stale -- forward,
+    load_weights, forward equals a freshly built model that loaded the same file (darknet.py:251-297)."""
+    torch.manual_seed(5)
+    src = Darknet(cfg_path)
+    f = str(tmp_path / "w.weights")
+    src.save_weights(f)
+    x = synth.images(1, seed=12).cuda()
+    torch.manual_seed(6)
+    m = Darknet(cfg_path).cuda().eval()
+    with torch.no_grad():
+        before = m(x).clone()
+        m.load_weights(f)
+        after = m(x).clone()
+    fresh = Darknet(cfg_path)
+    fresh.load_weights(f)
+    fresh = fresh.cuda().eval()
+    with torch.no_grad():
+        want = fresh(x)
+    assert torch.equal(after, want)
+    assert not torch.equal(before, after)
+
+
+def test_fused_sgd_repack_and_bucketed_step_match_plain(cfg_path, monkeypatch):
+    """FlatSGD's fused update + operand-plane rewrite (csrc/sgd_pack.cu), also issued bucket by bucket in reverse layer order
+    (the data-parallel overlap path, world size 1 here), gives the weights AND the next forward of the unfused path
+    (ssp_sgd_step_flat, re-pack at the next forward)."""
+    torch.manual_seed(7)
+    base = Darknet(cfg_path).cuda().train()
+    x, tgt = synth.images(2, seed=13).cuda(), synth.targets(2, seed=14)
+    crit = RegionLoss(); crit.verbose = False
+    outs = []
+    for mode in ("plain", "fused", "bucketed"):
+        m = copy.deepcopy(base)
+        opt = FlatSGD(m, lr=1e-4, momentum=0.9, weight_decay=0.032)
+        opt.fused = mode != "plain"
+        logits = []
+        for it in range(2):
+            opt.zero_grad()
+            o = m(x)
+            logits.append(o.detach().clone())
+            crit(o, tgt, 20).backward()
+            if mode == "bucketed" and it == 0:
+                opt.overlap_all_reduce(4)
+                assert len(opt._buckets) == 4 and opt._buckets[-1][1][0] == 0 and opt._buckets[0][1][1] == m._engine.flat_params.numel()
+                assert all(a[1][0] == b[1][1] for a, b in zip(opt._buckets[:-1], opt._buckets[1:]))     # contiguous, last layers first
+            opt.all_reduce_grads()
+            opt.step()
+        outs.append((logits, [p.detach().clone() for p in m.parameters()]))
+    for logits, params in outs[1:]:
+        assert torch.equal(logits[0], outs[0][0][0])
+        for p, q in zip(params, outs[0][1]):
+            assert _rel(p, q) < 1e-6
+        assert _rel(logits[1], outs[0][0][1]) < 1e-4          # second forward used the planes the optimiser wrote

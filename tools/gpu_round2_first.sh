@@ -6,10 +6,11 @@
 #  3. TMA fill rate per SM with own tiles / shared tiles / cluster multicast (tools/probes/mc_probe.cu)
 mkdir -p gpurun_out
 SSP_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_network.py -q -k "wgrad_pair or pack_weights_v2 or fused_bn_backward or other_resolutions_match" --timeout 300 2>&1 | tail -6
-for impl in tc tc2 tc tc2 v2pack bnfuse; do
+for impl in tc tc2 tc tc2 v2pack bnfuse sgdplain; do
   w=$impl
   if [ $impl = v2pack ]; then export SSP_PACK=v2; w=tc; fi
   if [ $impl = bnfuse ]; then unset SSP_PACK; export SSP_FUSE_BNBWD=1; w=tc; fi
+  if [ $impl = sgdplain ]; then unset SSP_FUSE_BNBWD; export SSP_SGD_FUSED=0; w=tc; fi
   SSP_WGRAD_IMPL=$w timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-pnp 2>/dev/null > gpurun_out/ab_$impl.json
   python - "$impl" <<'PY'
 import json, sys
