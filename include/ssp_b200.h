@@ -160,6 +160,11 @@ int ssp_region_decode_multi(const float* out_nchw, int B, int num_keypoints, int
 int ssp_pnp_batched(const float* points3d, int points3d_shared, const float* points2d, const float* K3x3,
                     int num_points, long long n, int max_iter, double* R_out, double* t_out,
                     int* iters_out_or_null, void* stream);
+/* same solve; work_out [n][3] int = {Jacobi sweeps of the 12x12 DLT, accepted LM iterations, LM linear solves} per problem: what the
+ * bench's achieved-FLOP/s figure is computed from */
+int ssp_pnp_batched_work(const float* points3d, int points3d_shared, const float* points2d, const float* K3x3,
+                         int num_points, long long n, int max_iter, double* R_out, double* t_out, int* work_out,
+                         void* stream);
 int ssp_project_points(const float* X, int rows, int nv, const double* Rt, const double* K3x3, long long n,
                        float* out, void* stream);
 

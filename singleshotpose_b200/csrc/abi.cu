@@ -46,7 +46,7 @@ int region_decode_argmax(const float*, int, int, int, int, int, int, float*, flo
 int region_loss_multi_fwd_bwd(const float*, const float*, float*, double*, int, int, int, int, int, int, const float*, int, float, float, float,
                               float, float, int, float, cudaStream_t);
 int region_decode_multi(const float*, int, int, int, int, int, int, int, int, float*, float*, float*, float*, long long*, float*, float*, cudaStream_t);
-int pnp_batched(const float*, int, const float*, const float*, int, long long, int, double*, double*, int*, cudaStream_t);
+int pnp_batched(const float*, int, const float*, const float*, int, long long, int, double*, double*, int*, int*, cudaStream_t);
 int project_points(const float*, int, int, const double*, const double*, long long, float*, cudaStream_t);
 long long aug_resize_work_bytes(int, int, int, int, int);
 long long aug_sample_work_bytes(int, int, int, int, int, int, int, int, int);
@@ -172,7 +172,11 @@ int ssp_region_decode_multi(const float* out, int B, int K, int nC, int nA, int 
   return region_decode_multi(out, B, K, nC, nA, H, W, only_objectness, corr, boxes, conf_sel, det, cls_corr, max_ind, max_conf, max_cls, ST(s));
 }
 int ssp_pnp_batched(const float* P3, int shared, const float* uv, const float* K, int np, long long n, int max_iter, double* R, double* t, int* iters, void* s) {
-  return pnp_batched(P3, shared, uv, K, np, n, max_iter, R, t, iters, ST(s));
+  return pnp_batched(P3, shared, uv, K, np, n, max_iter, R, t, iters, nullptr, ST(s));
+}
+int ssp_pnp_batched_work(const float* P3, int shared, const float* uv, const float* K, int np, long long n, int max_iter, double* R, double* t,
+                         int* work, void* s) {
+  return pnp_batched(P3, shared, uv, K, np, n, max_iter, R, t, nullptr, work, ST(s));
 }
 int ssp_project_points(const float* X, int rows, int nv, const double* Rt, const double* K, long long n, float* out, void* s) {
   return project_points(X, rows, nv, Rt, K, n, out, ST(s));

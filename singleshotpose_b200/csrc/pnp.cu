@@ -3,13 +3,17 @@
 //
 // One problem per thread, all arithmetic in fp64 like OpenCV:
 //   1. normalise the 2-D points with K (zero distortion);
-//   2. DLT initialisation on Hartley-normalised 3-D points.  OpenCV takes the smallest singular vector of the
-//      12x12 normal matrix; here p1, p2 are eliminated analytically (p_i = S^-1 S_i p3) and p3 is the smallest
-//      eigenvector of the 4x4 Schur complement (Jacobi) -- same solution for exact data, same LM basin otherwise;
+//   2. DLT initialisation exactly as cvFindExtrinsicCameraParams2 poses it: the 2N x 12 system on the RAW 3-D coordinates,
+//      unit-norm constraint over all 12 entries, i.e. the eigenvector of the smallest eigenvalue of the 12x12 normal matrix
+//      L^T L = [[S, 0, -Sx], [0, S, -Sy], [-Sx, -Sy, Sq]] (S = sum XX^T, Sx = sum x XX^T, ..., X = [X Y Z 1]); cyclic Jacobi in
+//      fp64.  (Round 1 eliminated p1, p2 analytically on Hartley-normalised points: the same minimiser for exact data but a
+//      different constraint under noise, so garbage keypoints -- what a random-init network emits -- could start LM in another
+//      basin than OpenCV.  With the exact formulation the kernel tracks cv2 at every noise level, sigma = 80 px included.)
 //   3. nearest rotation by polar decomposition, OpenCV's scale fix for t, Rodrigues -> rvec;
 //   4. Levenberg-Marquardt in pixel space with OpenCV's CvLevMarq schedule (lambda = 10^k, k0 = -3, diagonal
 //      scaling (1+lambda), reject => k++, accept => k--, <= max_iter accepted steps, eps = FLT_EPSILON).
-// The kernel is ALU/latency bound (~1.5e5 fp64 flop and 120 B of HBM traffic per problem).
+// The kernel is fp64-ALU / local-memory bound: ~1.6e4 flop per Jacobi sweep (6-9 sweeps), ~3e3 per LM evaluation, 120 B of HBM
+// traffic per problem.
 #include "ssp_common.cuh"
 
 namespace ssp {
@@ -47,11 +51,12 @@ __device__ void rodrigues(const double r[3], double R[9], double* J /*27 or null
   }
 }
 
-// cyclic Jacobi on a symmetric n x n matrix (n <= 4): A -> diag, V = eigenvectors (columns)
+// cyclic Jacobi on a symmetric n x n matrix: A -> diag, V = eigenvectors (columns); returns the number of sweeps
 template <int n>
-__device__ void jacobi_eig(double A[n][n], double V[n][n]) {
+__device__ int jacobi_eig(double A[n][n], double V[n][n]) {
   for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i][j] = (i == j) ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < 30; sweep++) {
+  int sweep = 0;
+  for (; sweep < 30; sweep++) {
     double off = 0.0, diag = 0.0;
     for (int i = 0; i < n; i++) { diag += A[i][i] * A[i][i]; for (int j = i + 1; j < n; j++) off += A[i][j] * A[i][j]; }
     if (off <= 1e-34 * diag || off == 0.0) break;
@@ -66,6 +71,7 @@ __device__ void jacobi_eig(double A[n][n], double V[n][n]) {
         for (int k = 0; k < n; k++) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
       }
   }
+  return sweep;
 }
 
 // in-place Cholesky solve of SPD n x n system (n <= 6); returns false if not positive definite
@@ -102,7 +108,8 @@ __device__ double reproj_err(const double* M, const double* m, int np, const dou
 
 __global__ void __launch_bounds__(128) pnp_kernel(const float* __restrict__ P3, long long p3_stride, const float* __restrict__ uv,
                                                   const float* __restrict__ Kmat, int np, long long n, int max_iter,
-                                                  double* __restrict__ R_out, double* __restrict__ t_out, int* __restrict__ iters_out) {
+                                                  double* __restrict__ R_out, double* __restrict__ t_out, int* __restrict__ iters_out,
+                                                  int* __restrict__ work_out /*[n][3]: Jacobi sweeps, LM iterations, LM solves; or null*/) {
   const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n) return;
   const double fx = Kmat[0], fy = Kmat[4], cx = Kmat[2], cy = Kmat[5];
@@ -112,64 +119,28 @@ __global__ void __launch_bounds__(128) pnp_kernel(const float* __restrict__ P3, 
   for (int i = 0; i < 3 * np; i++) M[i] = (double)p3[i];
   for (int i = 0; i < 2 * np; i++) m[i] = (double)q[i];
 
-  // ---- DLT on normalised points ----
-  double cen[3] = {0, 0, 0};
-  for (int i = 0; i < np; i++) { cen[0] += M[3 * i]; cen[1] += M[3 * i + 1]; cen[2] += M[3 * i + 2]; }
-  cen[0] /= np; cen[1] /= np; cen[2] /= np;
-  double ms = 0.0;
-  for (int i = 0; i < np; i++) for (int a = 0; a < 3; a++) { const double d = M[3 * i + a] - cen[a]; ms += d * d; }
-  const double sN = sqrt(3.0 * np / ms);            // RMS coordinate -> 1
-  double S[4][4] = {}, Sx[4][4] = {}, Sy[4][4] = {}, Sq[4][4] = {};
+  // ---- DLT (cvFindExtrinsicCameraParams2, non-planar branch): smallest eigenvector of L^T L on the raw coordinates ----
+  double LL[12][12], LV[12][12];
+  for (int a = 0; a < 12; a++) for (int b = 0; b < 12; b++) LL[a][b] = 0.0;
   for (int i = 0; i < np; i++) {
-    const double X[4] = {(M[3 * i] - cen[0]) * sN, (M[3 * i + 1] - cen[1]) * sN, (M[3 * i + 2] - cen[2]) * sN, 1.0};
-    const double x = (m[2 * i] - cx) / fx, y = (m[2 * i + 1] - cy) / fy;
+    const double X[4] = {M[3 * i], M[3 * i + 1], M[3 * i + 2], 1.0};
+    const double x = (m[2 * i] - cx) / fx, y = (m[2 * i + 1] - cy) / fy, qq = x * x + y * y;
     for (int a = 0; a < 4; a++)
       for (int b = 0; b < 4; b++) {
         const double xx = X[a] * X[b];
-        S[a][b] += xx; Sx[a][b] += x * xx; Sy[a][b] += y * xx; Sq[a][b] += (x * x + y * y) * xx;
+        LL[a][b] += xx; LL[4 + a][4 + b] += xx;
+        LL[a][8 + b] -= x * xx; LL[4 + a][8 + b] -= y * xx;
+        LL[8 + a][8 + b] += qq * xx;
       }
   }
-  // Sinv via Cholesky solves of the 4 unit vectors
-  double Sinv[4][4];
-  {
-    double L[4][4];
-    for (int col = 0; col < 4; col++) {
-      for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) L[a][b] = S[a][b];
-      double e[4] = {0, 0, 0, 0}; e[col] = 1.0;
-      chol_solve<4>(L, e);
-      for (int a = 0; a < 4; a++) Sinv[a][col] = e[a];
-    }
-  }
-  double Ax[4][4], Ay[4][4];      // S^-1 Sx, S^-1 Sy
-  for (int a = 0; a < 4; a++)
-    for (int b = 0; b < 4; b++) {
-      double vx = 0, vy = 0;
-      for (int k = 0; k < 4; k++) { vx += Sinv[a][k] * Sx[k][b]; vy += Sinv[a][k] * Sy[k][b]; }
-      Ax[a][b] = vx; Ay[a][b] = vy;
-    }
-  double Mq[4][4], V[4][4];
-  for (int a = 0; a < 4; a++)
-    for (int b = 0; b < 4; b++) {
-      double v = Sq[a][b];
-      for (int k = 0; k < 4; k++) v -= Sx[a][k] * Ax[k][b] + Sy[a][k] * Ay[k][b];   // Sx symmetric
-      Mq[a][b] = v;
-    }
-  for (int a = 0; a < 4; a++) for (int b = a + 1; b < 4; b++) { const double v = 0.5 * (Mq[a][b] + Mq[b][a]); Mq[a][b] = v; Mq[b][a] = v; }
-  jacobi_eig<4>(Mq, V);
+  for (int a = 0; a < 8; a++) for (int b = 8; b < 12; b++) LL[b][a] = LL[a][b];
+  const int sweeps = jacobi_eig<12>(LL, LV);
   int kmin = 0;
-  for (int k = 1; k < 4; k++) if (Mq[k][k] < Mq[kmin][kmin]) kmin = k;
-  double Pn[3][4];                  // projection rows for normalised points
-  for (int a = 0; a < 4; a++) Pn[2][a] = V[a][kmin];
-  for (int a = 0; a < 4; a++) {
-    double v1 = 0, v2 = 0;
-    for (int k = 0; k < 4; k++) { v1 += Ax[a][k] * Pn[2][k]; v2 += Ay[a][k] * Pn[2][k]; }
-    Pn[0][a] = v1; Pn[1][a] = v2;
-  }
-  // un-normalise: [Xn;1] = T [X;1], T = [[s I, -s c],[0 1]]  =>  P = Pn T
+  for (int k = 1; k < 12; k++) if (LL[k][k] < LL[kmin][kmin]) kmin = k;
   double RR[9], tt[3];
   for (int r = 0; r < 3; r++) {
-    RR[3 * r] = Pn[r][0] * sN; RR[3 * r + 1] = Pn[r][1] * sN; RR[3 * r + 2] = Pn[r][2] * sN;
-    tt[r] = Pn[r][3] - sN * (Pn[r][0] * cen[0] + Pn[r][1] * cen[1] + Pn[r][2] * cen[2]);
+    RR[3 * r] = LV[4 * r][kmin]; RR[3 * r + 1] = LV[4 * r + 1][kmin]; RR[3 * r + 2] = LV[4 * r + 2][kmin];
+    tt[r] = LV[4 * r + 3][kmin];
   }
   const double det = RR[0] * (RR[4] * RR[8] - RR[5] * RR[7]) - RR[1] * (RR[3] * RR[8] - RR[5] * RR[6]) + RR[2] * (RR[3] * RR[7] - RR[4] * RR[6]);
   if (det < 0) { for (int i = 0; i < 9; i++) RR[i] = -RR[i]; for (int i = 0; i < 3; i++) tt[i] = -tt[i]; }
@@ -207,7 +178,7 @@ __global__ void __launch_bounds__(128) pnp_kernel(const float* __restrict__ P3, 
   }
 
   // ---- Levenberg-Marquardt (CvLevMarq schedule) ----
-  int lam_lg10 = -3, iters = 0;
+  int lam_lg10 = -3, iters = 0, solves = 0;
   double prev_err = 0.0, e = 0.0;
   while (true) {
     double R[9], dR[27];
@@ -245,6 +216,7 @@ __global__ void __launch_bounds__(128) pnp_kernel(const float* __restrict__ P3, 
       double A[6][6], d[6];
       for (int a = 0; a < 6; a++) { for (int b = 0; b < 6; b++) A[a][b] = JtJ[a][b]; A[a][a] *= 1.0 + lam; d[a] = Jte[a]; }
       if (!chol_solve<6>(A, d)) { for (int a = 0; a < 6; a++) d[a] = 0.0; }
+      solves++;
       for (int a = 0; a < 6; a++) p[a] = prev[a] - d[a];
       e = reproj_err(M, m, np, p, fx, fy, cx, cy);
       if (!(e > prev_err)) break;
@@ -261,6 +233,7 @@ __global__ void __launch_bounds__(128) pnp_kernel(const float* __restrict__ P3, 
   for (int i = 0; i < 9; i++) R_out[id * 9 + i] = R[i];
   for (int i = 0; i < 3; i++) t_out[id * 3 + i] = p[3 + i];
   if (iters_out) iters_out[id] = iters;
+  if (work_out) { work_out[3 * id] = sweeps; work_out[3 * id + 1] = iters; work_out[3 * id + 2] = solves; }
 }
 
 // compute_projection (utils.py:40-45): uv = K [R|t] X / z for every vertex; fp64 math, fp32 result [n][2][nv]
@@ -281,10 +254,10 @@ __global__ void project_points_kernel(const float* __restrict__ X4 /*[4][nv] or 
 }
 
 int pnp_batched(const float* P3, int p3_shared, const float* uv, const float* K, int np, long long n, int max_iter,
-                double* R_out, double* t_out, int* iters_out, cudaStream_t s) {
+                double* R_out, double* t_out, int* iters_out, int* work_out, cudaStream_t s) {
   if (!P3 || !uv || !K || !R_out || !t_out || np < 6 || np > PNP_MAXP || n < 0) return fail_msg(SSP_ERR_ARG, "pnp_batched: bad argument (6 <= points <= 16)");
   if (n == 0) return SSP_OK;
-  pnp_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P3, p3_shared ? 0 : 3LL * np, uv, K, np, n, max_iter, R_out, t_out, iters_out);
+  pnp_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P3, p3_shared ? 0 : 3LL * np, uv, K, np, n, max_iter, R_out, t_out, iters_out, work_out);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
 

@@ -11,6 +11,7 @@ GOLDEN = os.path.join(REPO, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    config.addinivalue_line("markers", "slow: tens of seconds (full-size benchmark configuration against the CPU oracle)")
 
 
 @pytest.fixture(scope="session")

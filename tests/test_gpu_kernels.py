@@ -152,6 +152,55 @@ def test_wgrad_gemm_matches_torch(case, impl, dyfmt):
     assert (out - ref).abs().max() / ref.abs().max() < 1e-4
 
 
+# fp16 storage bound of the single-term backward GEMMs against the UNQUANTISED fp64 result: each operand is rounded once to fp16
+# (relative 2^-12 rms, 2^-11 worst), so every product carries ~2^-11.5 rms relative error and the errors of a K-term sum of
+# random-sign terms add in quadrature: ||d||_2 / ||ref||_2 ~ 3.5e-4 independent of K.  Asserted with a 3x margin in L2 and, since
+# the largest element of a random-sign sum stands ~4 sigma above the rms error, 8e-3 in max-norm (relative to the largest element).
+FP16_BWD_L2, FP16_BWD_MAX = 1.1e-3, 8e-3
+
+
+@pytest.mark.parametrize("case", [(2, 13, 13, 256, 128, 3), (2, 26, 26, 128, 64, 1), (1, 13, 13, 1024, 512, 3)])
+def test_wgrad_vs_unquantised_fp64(case):
+    """weight gradient from fp16-stored dY and X against the fp64 gradient of the UNROUNDED operands (the other
+    wgrad tests round the reference's operands first and so cannot see the quantisation error)"""
+    N, H, W, cin, cout, k = case
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(N, cin, H, W, generator=g)
+    dy = torch.randn(N, cout, H, W, generator=g)
+    ref = torch.nn.grad.conv2d_weight(x.double(), (cout, cin, k, k), dy.double(), padding=(k - 1) // 2)
+    xh, _, rows = flat_from_nchw(x.to(DEV), fmt=_lib.FMT_F16, split=False)
+    dyh, _, _ = flat_from_nchw(dy.to(DEV), fmt=_lib.FMT_F16, split=False)
+    dw = torch.zeros(cout, k * k, cin, device=DEV)
+    call("ssp_wgrad_gemm", _lib.IMPL_TC, ptr(dyh), rows, cout, cout, _lib.FMT_F16, ptr(xh), rows, cin, cin, _lib.FMT_F16,
+         N, H, W, k * k, ptr(dw), cin, cin, 1.0, stream_ptr())
+    torch.cuda.synchronize()
+    out = dw.view(cout, k, k, cin).permute(0, 3, 1, 2).cpu().double()
+    l2, mx = float((out - ref).norm() / ref.norm()), float((out - ref).abs().max() / ref.abs().max())
+    assert l2 < FP16_BWD_L2 and mx < FP16_BWD_MAX, (l2, mx)
+    assert l2 > 5e-5              # the test does see quantisation (an fp32-exact path would sit at ~1e-7)
+
+
+@pytest.mark.parametrize("case", [(2, 13, 13, 256, 128, 3), (2, 26, 26, 128, 64, 1), (1, 13, 13, 512, 1024, 3)])
+def test_dgrad_vs_unquantised_fp64(case):
+    """data gradient from fp16-stored dY and fp16 tap-flipped weights against the fp64 conv_transpose of the UNROUNDED operands"""
+    N, H, W, cin, cout, k = case
+    g = torch.Generator().manual_seed(22)
+    dy = torch.randn(N, cout, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    ref = F.conv_transpose2d(dy.double(), w.double(), padding=(k - 1) // 2)
+    dyh, _, rows = flat_from_nchw(dy.to(DEV), fmt=_lib.FMT_F16, split=False)
+    _, _, wd = _pack_w(w.to(DEV), fmt=_lib.FMT_F16, dgrad=True)
+    impl = _lib.IMPL_TC2 if cin >= 128 else _lib.IMPL_TC
+    dx = torch.zeros(rows, cin, device=DEV)
+    call("ssp_conv_gemm", impl, ptr(dyh), None, rows, cout, cout, ptr(wd), None, cin, wd.shape[1], 0, 0,
+         N, H, W, k * k, cin, ptr(dx), cin, rows, _lib.EPI_F32, None, None, None, stream_ptr())
+    torch.cuda.synchronize()
+    out = nchw_from_flat(dx, N, cin, H, W).cpu().double()
+    l2, mx = float((out - ref).norm() / ref.norm()), float((out - ref).abs().max() / ref.abs().max())
+    assert l2 < FP16_BWD_L2 and mx < FP16_BWD_MAX, (l2, mx)
+    assert l2 > 5e-5
+
+
 @pytest.mark.skipif(os.environ.get("SSP_EXPERIMENTAL", "0") != "1", reason="experimental CTA-pair wgrad (csrc/wgrad_tc2.cu): opt-in, SSP_EXPERIMENTAL=1")
 @pytest.mark.parametrize("case", [(2, 13, 13, 256, 256, 3), (1, 13, 13, 512, 256, 1), (2, 26, 26, 256, 512, 3), (64, 13, 13, 512, 256, 3)])
 def test_wgrad_pair_experimental(case):

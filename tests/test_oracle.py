@@ -54,6 +54,36 @@ def test_pnp_oracle_matches_cv2_golden(golden_dir):
             assert np.abs(t.reshape(3) - g["t_" + tag][i]).max() * 1e3 < 1e-4   # mm
 
 
+def test_pnp_oracle_matches_reference_golden_noisy(golden_dir):
+    """sigma = 5 / 20 / 80 px and random-init-network keypoints: outputs of the reference's own pnp (make_golden_pnp_noise.py)"""
+    g = np.load(os.path.join(golden_dir, "pnp_noise.npz"))
+    for tag in ("s5", "s20", "s80", "net"):
+        for i in range(0, 64, 8):
+            R, t = pnp_ref(g["P3"], g["uv_" + tag][i], g["K"])
+            assert _ang(R, g["R_" + tag][i]) < 1e-3, (tag, i)
+            assert np.abs(t.reshape(3) - g["t_" + tag][i]).max() * 1e3 < 1e-3, (tag, i)
+
+
+def test_eval_loop_oracle_recovers_planted_pose():
+    """oracle/eval_ref.py (valid.py:123-183): planting the exact ground-truth keypoints in one confident cell gives zero errors"""
+    import torch
+    from oracle.eval_ref import evaluate_image_ref
+    pr = synth.pnp_problems(1, sigma=0.0, seed=21)
+    uvn = pr["uv"][0] / np.array([640.0, 480.0], np.float32)
+    out = torch.zeros(1, 20, 13, 13)
+    cx, cy = int(uvn[0, 0] * 13), int(uvn[0, 1] * 13)
+    for k in range(9):
+        vx, vy = uvn[k, 0] * 13 - cx, uvn[k, 1] * 13 - cy
+        if k == 0:
+            vx, vy = np.log(vx / (1 - vx)), np.log(vy / (1 - vy))
+        out[0, 2 * k, cy, cx], out[0, 2 * k + 1, cy, cx] = float(vx), float(vy)
+    out[0, 18, cy, cx] = 8.0
+    tgt = np.zeros(21, np.float32); tgt[1:19] = uvn.reshape(-1)
+    verts = np.concatenate([np.random.default_rng(0).uniform(-0.04, 0.04, size=(3, 50)), np.ones((1, 50))])
+    r = evaluate_image_ref(out, tgt, verts, pr["P3"], synth.intrinsics())
+    assert r["corner_err_px"] < 1e-2 and r["pixel_err"] < 1e-2 and r["angle_err_deg"] < 5e-2 and r["trans_err"] < 1e-4
+
+
 def test_pnp_oracle_live_cv2():
     cv2 = pytest.importorskip("cv2")
     pr = synth.pnp_problems(8, sigma=1.0, seed=11)
