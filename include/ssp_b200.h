@@ -89,9 +89,13 @@ int ssp_wgrad_gemm(int impl, const void* dy, long long dy_rows, int dy_ld, int c
 int ssp_bn_finalize(double* stat_sum, double* stat_sq, double count, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float momentum, float eps, int train, float* mean,
                     float* invstd, float* scale, float* shift, int C, void* stream);
+/* ypool (optional, max-pool destinations only): fp32 plane in the POOLED geometry receiving the conv output y at the arg-max
+ * position of every 2x2 window.  With it the first pass of the BN backward of a pooled layer runs at a quarter of the
+ * resolution: ssp_bn_bwd_reduce(y = ypool, H/2, W/2, g0 = pooled upstream gradient, SSP_ROUTE_DIRECT) accumulates the same
+ * S1 / S2 as the full-resolution call (only arg-max positions receive gradient). */
 int ssp_bn_apply(const float* y, int y_ld, const float* scale, const float* shift, int N, int C, int H, int W,
                  float slope, void* d0_hi, void* d0_lo, int d0_ld, int d0_c0, int d0_route, void* d1_hi, void* d1_lo,
-                 int d1_ld, int d1_c0, int d1_route, void* stream);
+                 int d1_ld, int d1_c0, int d1_route, float* ypool_or_null, int ypool_ld, void* stream);
 int ssp_bn_bwd_reduce(const float* y, int y_ld, const float* scale, const float* shift, const float* mean,
                       const float* invstd, const float* gamma, int N, int C, int H, int W, float slope,
                       const float* g0, int g0_ld, int g0_c0, int g0_route, const float* g1, int g1_ld, int g1_c0,

@@ -31,7 +31,7 @@ SIGNATURES = {
     "ssp_conv_gemm_dgrad_bnred": [_p, _ll, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _ll, _p, _i, _p, _p, _p, _p, _f, _i, _i, _p, _p, _p],
     "ssp_wgrad_gemm": [_i, _p, _ll, _i, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _f, _p],
     "ssp_bn_finalize": [_p, _p, _d, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _i, _p],
-    "ssp_bn_apply": [_p, _i, _p, _p, _i, _i, _i, _i, _f, _p, _p, _i, _i, _i, _p, _p, _i, _i, _i, _p],
+    "ssp_bn_apply": [_p, _i, _p, _p, _i, _i, _i, _i, _f, _p, _p, _i, _i, _i, _p, _p, _i, _i, _i, _p, _i, _p],
     "ssp_bn_bwd_reduce": [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p],
     "ssp_bn_bwd_apply": [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p, _i, _i, _f, _p],
     "ssp_bn_bwd_finalize": [_p, _p, _p, _p, _i, _i, _f, _p],

@@ -30,7 +30,7 @@ int pack_nchw(const float*, void*, void*, int, int, int, int, int, int, int, flo
 int unpack_nchw(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int unpack16_nchw(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int bn_finalize(double*, double*, double, const float*, const float*, float*, float*, float, float, int, float*, float*, float*, float*, int, cudaStream_t);
-int bn_apply(const float*, int, const float*, const float*, int, int, int, int, float, void*, void*, int, int, int, void*, void*, int, int, int, cudaStream_t);
+int bn_apply(const float*, int, const float*, const float*, int, int, int, int, float, void*, void*, int, int, int, void*, void*, int, int, int, float*, int, cudaStream_t);
 int bn_bwd_reduce(const float*, int, const float*, const float*, const float*, const float*, const float*, int, int, int, int, float,
                   const float*, int, int, int, const float*, int, int, int, double*, double*, cudaStream_t);
 int bn_bwd_apply(const float*, int, const float*, const float*, const float*, const float*, const float*, int, int, int, int, float,
@@ -124,8 +124,9 @@ int ssp_bn_finalize(double* ssum, double* ssq, double count, const float* gamma,
   return bn_finalize(ssum, ssq, count, gamma, beta, rm, rv, momentum, eps, train, mean, invstd, scale, shift, C, ST(s));
 }
 int ssp_bn_apply(const float* y, int y_ld, const float* scale, const float* shift, int N, int C, int H, int W, float slope,
-                 void* d0_hi, void* d0_lo, int d0_ld, int d0_c0, int d0_route, void* d1_hi, void* d1_lo, int d1_ld, int d1_c0, int d1_route, void* s) {
-  return bn_apply(y, y_ld, scale, shift, N, C, H, W, slope, d0_hi, d0_lo, d0_ld, d0_c0, d0_route, d1_hi, d1_lo, d1_ld, d1_c0, d1_route, ST(s));
+                 void* d0_hi, void* d0_lo, int d0_ld, int d0_c0, int d0_route, void* d1_hi, void* d1_lo, int d1_ld, int d1_c0, int d1_route,
+                 float* ypool, int ypool_ld, void* s) {
+  return bn_apply(y, y_ld, scale, shift, N, C, H, W, slope, d0_hi, d0_lo, d0_ld, d0_c0, d0_route, d1_hi, d1_lo, d1_ld, d1_c0, d1_route, ypool, ypool_ld, ST(s));
 }
 int ssp_bn_bwd_reduce(const float* y, int y_ld, const float* scale, const float* shift, const float* mean, const float* invstd, const float* gamma,
                       int N, int C, int H, int W, float slope, const float* g0, int g0_ld, int g0_c0, int g0_route,

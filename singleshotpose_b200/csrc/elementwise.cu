@@ -152,6 +152,7 @@ struct BnApplyParams {
   int N, C, H, W;
   float slope;          // 0.1 leaky, 1.0 linear
   ActDst dst[2];
+  float* ypool; int ypool_ld;   // POOLED only, optional: conv output y at the arg-max position of every 2x2 window (fp32, pooled geometry)
 };
 
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
@@ -229,14 +230,19 @@ __global__ void SSP_BN_BOUNDS bn_apply_kernel(const BnApplyParams p) {
     for (int t = 0; t < UNR; t++) {
       if (!ok[t]) continue;
       float zmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      float ybest[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int q = 0; q < NP; q++) {
         const int h = POOLED ? hh[t] * 2 + (q >> 1) : hh[t], w = POOLED ? ww[t] * 2 + (q & 1) : ww[t];
         const float4 v = yv[t][q];
         float z[4] = {leaky(fmaf(v.x, sc.x, sh.x), p.slope), leaky(fmaf(v.y, sc.y, sh.y), p.slope),
                       leaky(fmaf(v.z, sc.z, sh.z), p.slope), leaky(fmaf(v.w, sc.w, sh.w), p.slope)};
+        if (POOLED) {
+          // the first maximum of the ACTIVATED values in (h, w) scan order wins -- the rule of bn_bwd's arg-max (max_pool2d semantics)
+          const float yq[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; j++) zmax[j] = fmaxf(zmax[j], z[j]);
+          for (int j = 0; j < 4; j++) if (z[j] > zmax[j]) { zmax[j] = z[j]; ybest[j] = yq[j]; }
+        }
 #pragma unroll
         for (int d = 0; d < 2; d++) {
           if (p.dst[d].kind == DST_DIRECT) store4(p.dst[d], rows[t][q], c, z);
@@ -248,6 +254,8 @@ __global__ void SSP_BN_BOUNDS bn_apply_kernel(const BnApplyParams p) {
 #pragma unroll
         for (int d = 0; d < 2; d++)
           if (p.dst[d].kind == DST_POOL) store4(p.dst[d], gh.row(nn[t], hh[t], ww[t]), c, zmax);
+        if (p.ypool)
+          *reinterpret_cast<float4*>(p.ypool + gh.row(nn[t], hh[t], ww[t]) * p.ypool_ld + c) = make_float4(ybest[0], ybest[1], ybest[2], ybest[3]);
       }
     }
   }
@@ -544,13 +552,16 @@ int bn_finalize(double* ssum, double* ssq, double count, const float* gamma, con
 }
 int bn_apply(const float* y, int y_ld, const float* scale, const float* shift, int N, int C, int H, int W, float slope,
              void* d0_hi, void* d0_lo, int d0_ld, int d0_c0, int d0_kind,
-             void* d1_hi, void* d1_lo, int d1_ld, int d1_c0, int d1_kind, cudaStream_t s) {
+             void* d1_hi, void* d1_lo, int d1_ld, int d1_c0, int d1_kind, float* ypool, int ypool_ld, cudaStream_t s) {
   if (!y || !scale || !shift || (C % 4)) return fail_msg(SSP_ERR_ARG, "bn_apply: bad argument (C must be a multiple of 4)");
+  if (ypool && ((ypool_ld % 4) || ypool_ld < C)) return fail_msg(SSP_ERR_ARG, "bn_apply: arg-max plane needs ld % 4 == 0 and ld >= C");
   BnApplyParams p;
   p.y = y; p.y_ld = y_ld; p.scale = scale; p.shift = shift; p.N = N; p.C = C; p.H = H; p.W = W; p.slope = slope;
   p.dst[0] = ActDst{(uint16_t*)d0_hi, (uint16_t*)d0_lo, d0_ld, d0_c0, d0_hi ? d0_kind : DST_NONE};
   p.dst[1] = ActDst{(uint16_t*)d1_hi, (uint16_t*)d1_lo, d1_ld, d1_c0, d1_hi ? d1_kind : DST_NONE};
   const bool pooled = p.dst[0].kind == DST_POOL || p.dst[1].kind == DST_POOL;
+  if (ypool && !pooled) return fail_msg(SSP_ERR_ARG, "bn_apply: the arg-max plane belongs to a max-pool destination");
+  p.ypool = ypool; p.ypool_ld = ypool_ld;
   const bool halves = pooled || p.dst[0].kind == DST_REORG || p.dst[1].kind == DST_REORG;
   if (halves && ((H | W) & 1)) return fail_msg(SSP_ERR_ARG, "bn_apply: pool/reorg need even H and W");
   if (pooled) bn_apply_kernel<true><<<unit_grid(C, (long long)N * (H / 2) * (W / 2), BN_UNITS_PER_THREAD), 256, 0, s>>>(p);

@@ -130,7 +130,7 @@ class Buffers:
         self.generation = 0
         f16 = torch.float16
         self.x_hi, self.x_lo, self.y, self.rows = [], [], [], []
-        self.dy, self.dx = [], []
+        self.dy, self.dx, self.ypool = [], [], []
         # per-layer BN state (batch sums, mean / invstd, folded scale / shift, backward sums) lives with the activations it
         # describes: a forward of another shape or mode between a training forward and its backward cannot overwrite it
         self.stat = []
@@ -147,6 +147,10 @@ class Buffers:
             self.x_lo.append(torch.zeros(rows, cin_total, dtype=f16, device=dev))
             self.y.append(torch.zeros(rows, _rup(L.cout, 4), dtype=torch.float32, device=dev))
             if train:
+                pooled = eng.compact_pool_reduce and any(k == _lib.ROUTE_POOL for (_c, _o, k) in L.dests)
+                # y at the arg-max of every 2x2 window (pooled geometry): the BN-backward reduction of a pooled layer reads this
+                # plane + the pooled gradient (8 B per window) instead of the four full-resolution y values + the gradient (20 B)
+                self.ypool.append(torch.zeros(_lib.flat_alloc_rows(N, h // 2, w // 2), _rup(L.cout, 4), dtype=torch.float32, device=dev) if pooled else None)
                 self.dy.append(torch.zeros(rows, _rup(L.cout, 8), dtype=eng.grad_dtype, device=dev))
                 self.dx.append(None if L.first else torch.zeros(rows, cin_total, dtype=torch.float32, device=dev))
 
@@ -184,6 +188,7 @@ class Engine:
         # experimental (opt-in, not yet measured): the BN-backward reduction of a producer with ONE direct consumer runs in the
         # epilogue of that consumer's data-gradient GEMM (csrc/conv_tc2.cu MODE 2) instead of as its own pass over Y and dX
         self.fuse_bnbwd = os.environ.get("SSP_FUSE_BNBWD", "0") == "1"
+        self.compact_pool_reduce = os.environ.get("SSP_POOL_REDUCE", "compact") != "full"
         self._direct_producer = {}
         for Lp in self.layers:
             if Lp.bn and len(Lp.dests) == 1 and Lp.dests[0][2] == _lib.ROUTE_DIRECT and Lp.cout % 32 == 0 and Lp.cout <= 1024 and Lp.dests[0][1] % 32 == 0:
@@ -447,7 +452,9 @@ class Engine:
                 d += [ptr(B.x_hi[ci]), ptr(B.x_lo[ci]), B.x_hi[ci].shape[1], c0, kind]
             if len(L.dests) == 1:
                 d += [None, None, 0, 0, _lib.ROUTE_NONE]
-            call("ssp_bn_apply", ptr(B.y[i]), B.y[i].shape[1], ptr(st["scale"]), ptr(st["shift"]), N, L.cout, h, w, L.slope, *d, s)
+            yp = B.ypool[i] if keep_for_backward else None
+            call("ssp_bn_apply", ptr(B.y[i]), B.y[i].shape[1], ptr(st["scale"]), ptr(st["shift"]), N, L.cout, h, w, L.slope, *d,
+                 ptr(yp), yp.shape[1] if yp is not None else 0, s)
             self.launches += 2
         last = self.layers[-1]
         h, w = self.spatial(last, H, W)
@@ -494,7 +501,24 @@ class Engine:
                     srcs += [None, 0, 0, _lib.ROUTE_NONE]
                 common = [ptr(B.y[i]), B.y[i].shape[1], ptr(st["scale"]), ptr(st["shift"]), ptr(st["mean"]), ptr(st["invstd"]),
                           ptr(bn.weight.data), N, L.cout, h, w, L.slope, *srcs, ptr(st["s1"]), ptr(st["s2"])]
-                if i not in reduced_in_dgrad:
+                yp = B.ypool[i]
+                if i in reduced_in_dgrad:
+                    pass
+                elif yp is not None:
+                    # pooled consumer(s): only the arg-max position of a 2x2 window receives gradient, so S1 / S2 are sums over
+                    # pooled cells -- reduce at a quarter of the resolution from the arg-max plane; S1 / S2 are linear in the
+                    # upstream gradient, so any other consumer (layer 16 also feeds the reorg branch) adds its own pass
+                    head = common[:7]
+                    for (ci, c0, kind) in L.dests:
+                        if kind == _lib.ROUTE_POOL:
+                            call("ssp_bn_bwd_reduce", ptr(yp), yp.shape[1], *head[2:], N, L.cout, h // 2, w // 2, L.slope,
+                                 ptr(B.dx[ci]), B.dx[ci].shape[1], c0, _lib.ROUTE_DIRECT, None, 0, 0, _lib.ROUTE_NONE, ptr(st["s1"]), ptr(st["s2"]), s)
+                        else:
+                            call("ssp_bn_bwd_reduce", *head, N, L.cout, h, w, L.slope, ptr(B.dx[ci]), B.dx[ci].shape[1], c0, kind,
+                                 None, 0, 0, _lib.ROUTE_NONE, ptr(st["s1"]), ptr(st["s2"]), s)
+                        self.launches += 1
+                    self.launches -= 1
+                else:
                     call("ssp_bn_bwd_reduce", *common, s)
                 call("ssp_bn_bwd_apply", *common, ptr(dy), dy.shape[1], self.grad_fmt, 1.0, s)
                 call("ssp_bn_bwd_finalize", ptr(st["s1"]), ptr(st["s2"]), ptr(self.grad_view(bn.weight)), ptr(self.grad_view(bn.bias)),

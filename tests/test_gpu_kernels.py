@@ -289,8 +289,9 @@ def test_bn_apply_and_backward(route, C):
     oN, oC, oH, oW = out_ref.shape
     orows = _lib.flat_alloc_rows(oN, oH, oW)
     ohi = torch.zeros(orows, oC, dtype=torch.float16, device=DEV); olo = torch.zeros_like(ohi)
+    ypool = torch.zeros(orows, C, device=DEV) if route == _lib.ROUTE_POOL else None
     call("ssp_bn_apply", ptr(yf), C, ptr(scale), ptr(shift), N, C, H, W, 0.1, ptr(ohi), ptr(olo), oC, 0, route,
-         None, None, 0, 0, 0, stream_ptr())
+         None, None, 0, 0, 0, ptr(ypool), C, stream_ptr())
     got = torch.empty(oN, oC, oH, oW, device=DEV)
     call("ssp_unpack16_nchw", ptr(ohi), ptr(olo), ptr(got), oN, oC, oH, oW, oC, 0, 0, stream_ptr())
     assert (got.cpu() - out_ref.detach()).abs().max() < 2e-5 * out_ref.detach().abs().max()
@@ -301,6 +302,14 @@ def test_bn_apply_and_backward(route, C):
     common = [ptr(yf), C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(gm), N, C, H, W, 0.1,
               ptr(gf), oC, 0, route, None, 0, 0, 0, ptr(s1), ptr(s2)]
     call("ssp_bn_bwd_reduce", *common, stream_ptr())
+    if ypool is not None:
+        # quarter-resolution first pass from the arg-max plane: the same S1 / S2 as the full-resolution reduction
+        t1 = torch.zeros_like(s1); t2 = torch.zeros_like(s2)
+        call("ssp_bn_bwd_reduce", ptr(ypool), C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(gm), N, C, H // 2, W // 2, 0.1,
+             ptr(gf), oC, 0, _lib.ROUTE_DIRECT, None, 0, 0, 0, ptr(t1), ptr(t2), stream_ptr())
+        torch.cuda.synchronize()
+        assert torch.allclose(t1, s1, rtol=1e-6, atol=1e-6 * float(s1.abs().max()))
+        assert torch.allclose(t2, s2, rtol=1e-6, atol=1e-6 * float(s2.abs().max()))
     dy = torch.zeros(rows, C, dtype=torch.float16, device=DEV)
     call("ssp_bn_bwd_apply", *common, ptr(dy), C, _lib.FMT_F16, 1.0, stream_ptr())
     dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
