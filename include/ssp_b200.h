@@ -196,6 +196,21 @@ int ssp_aug_sample(const void* img, const void* mask, int ow, int oh, const void
                    int pleft, int ptop, int cw, int ch, int out_w, int out_h, int resample, void* work,
                    long long work_bytes, void* out_u8_or_null, float* out_chw_or_null, void* stream);
 
+/* Batched form of ssp_aug_sample: ONE launch per pipeline stage for the whole batch (<= 10 launches instead of ~10 per sample).
+ *   ssp_aug_batch_plan (host only, no device access): items[n] hold the per-sample arguments of ssp_aug_sample with DEVICE
+ *     pointers (each sample its own work buffer of ssp_aug_sample_work_bytes()); writes the op table (table_bytes >=
+ *     ssp_aug_batch_table_bytes(n)) into HOST memory -- typically the tail of the pinned staging buffer, so that it travels in the
+ *     batch's single host->device copy -- and stage_dims[20].
+ *   ssp_aug_batch_run: table_dev = the device copy of that table; launches the stages on `stream`. */
+typedef struct ssp_aug_item {
+  const void* img; const void* mask; int ow, oh; const void* bg; int bw, bh; const void* luts; int pleft, ptop, cw, ch;
+  void* work; long long work_bytes; void* out_u8; float* out_chw;
+} ssp_aug_item;
+long long ssp_aug_batch_table_bytes(int n);
+int ssp_aug_batch_plan(const ssp_aug_item* items_host, int n, int out_w, int out_h, int resample, void* table_host,
+                       long long table_bytes, int* stage_dims_host20);
+int ssp_aug_batch_run(const void* table_dev, int n, const int* stage_dims_host20, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,9 @@ long long aug_sample_work_bytes(int, int, int, int, int, int, int, int, int);
 int aug_resize_u8(const uint8_t*, int, int, int, int, int, int, uint8_t*, int, int, int, uint8_t*, long long, cudaStream_t);
 int aug_convert_u8(const uint8_t*, uint8_t*, long long, int, cudaStream_t);
 int aug_to_tensor_u8(const uint8_t*, long long, float*, cudaStream_t);
+long long aug_batch_table_bytes(int);
+int aug_batch_plan(const ssp_aug_item*, int, int, int, int, void*, long long, int*);
+int aug_batch_run(const void*, int, const int*, cudaStream_t);
 int aug_sample(const uint8_t*, const uint8_t*, int, int, const uint8_t*, int, int, const uint8_t*, int, int, int, int, int, int, int, uint8_t*,
                long long, uint8_t*, float*, cudaStream_t);
 }  // namespace ssp
@@ -190,6 +193,11 @@ int ssp_aug_resize_u8(const void* src, int src_w, int src_h, int x0, int y0, int
 int ssp_aug_rgb2hsv_u8(const void* rgb, void* hsv, long long n_pixels, void* s) { return aug_convert_u8((const uint8_t*)rgb, (uint8_t*)hsv, n_pixels, 1, ST(s)); }
 int ssp_aug_hsv2rgb_u8(const void* hsv, void* rgb, long long n_pixels, void* s) { return aug_convert_u8((const uint8_t*)hsv, (uint8_t*)rgb, n_pixels, 2, ST(s)); }
 int ssp_aug_to_tensor_u8(const void* hwc, long long n_pixels, float* out_chw, void* s) { return aug_to_tensor_u8((const uint8_t*)hwc, n_pixels, out_chw, ST(s)); }
+long long ssp_aug_batch_table_bytes(int n) { return aug_batch_table_bytes(n); }
+int ssp_aug_batch_plan(const ssp_aug_item* items, int n, int out_w, int out_h, int resample, void* table_host, long long table_bytes, int* stage_dims) {
+  return aug_batch_plan(items, n, out_w, out_h, resample, table_host, table_bytes, stage_dims);
+}
+int ssp_aug_batch_run(const void* table_dev, int n, const int* stage_dims, void* s) { return aug_batch_run(table_dev, n, stage_dims, ST(s)); }
 long long ssp_aug_sample_work_bytes(int ow, int oh, int bw, int bh, int cw, int ch, int out_w, int out_h, int resample) {
   return aug_sample_work_bytes(ow, oh, bw, bh, cw, ch, out_w, out_h, resample);
 }

@@ -71,6 +71,13 @@ __global__ void aug_to_tensor_kernel(const uint8_t* __restrict__ src, long long 
   }
 }
 
+// one STAGE of a batch: op table column per sample (blockIdx.z), one thread per element of the op's (nx, ny) extent
+__global__ void __launch_bounds__(256) aug_stage_kernel(const AugOp* __restrict__ ops) {
+  const AugOp& op = ops[blockIdx.z];
+  if (op.kind == OP_NONE) return;
+  op_element(op, blockIdx.x * 32 + (threadIdx.x & 31), blockIdx.y * 8 + (threadIdx.x >> 5));
+}
+
 namespace {
 inline int blocks_for(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
@@ -138,6 +145,35 @@ int aug_to_tensor_u8(const uint8_t* src, long long n_px, float* out_chw, cudaStr
   if (!src || !out_chw || n_px < 0) return fail_msg(SSP_ERR_ARG, "ssp_aug_to_tensor_u8: bad argument");
   if (n_px == 0) return SSP_OK;
   aug_to_tensor_kernel<<<blocks_for(n_px, 256), 256, 0, s>>>(src, n_px, out_chw);
+  SSP_CHECK_LAUNCH();
+  return SSP_OK;
+}
+
+long long aug_batch_table_bytes(int n) { return n > 0 ? (long long)kMaxStages * n * (long long)sizeof(AugOp) : SSP_ERR_ARG; }
+
+// host side of the batched path: items (device pointers, host array) -> op table (host memory, to be copied to the device with the
+// batch) + per-stage launch extents
+int aug_batch_plan(const ssp_aug_item* items, int n, int out_w, int out_h, int resample, void* table_host, long long table_bytes, int* stage_dims) {
+  static_assert(sizeof(ssp_aug_item) == sizeof(AugItem), "ssp_aug_item (include/ssp_b200.h) must mirror AugItem (augment_core.h)");
+  if (!items || !table_host || !stage_dims || n <= 0 || table_bytes < aug_batch_table_bytes(n)) return fail_msg(SSP_ERR_ARG, "ssp_aug_batch_plan: bad argument");
+  for (int i = 0; i < n; i++)
+    if (!items[i].img || !items[i].mask || !items[i].bg || !items[i].luts || !items[i].work || (!items[i].out_u8 && !items[i].out_chw) ||
+        ((uintptr_t)items[i].work % 16))
+      return fail_msg(SSP_ERR_ARG, "ssp_aug_batch_plan: null pointer or misaligned work buffer in an item");
+  const int rc = augment_batch_plan(reinterpret_cast<const AugItem*>(items), n, out_w, out_h, resample, (AugOp*)table_host, stage_dims);
+  if (rc) return driver_rc(rc, "ssp_aug_batch_plan");
+  return SSP_OK;
+}
+
+int aug_batch_run(const void* table_dev, int n, const int* stage_dims, cudaStream_t s) {
+  if (!table_dev || !stage_dims || n <= 0 || n > 65535) return fail_msg(SSP_ERR_ARG, "ssp_aug_batch_run: bad argument");
+  const AugOp* ops = (const AugOp*)table_dev;
+  for (int st = 0; st < kMaxStages; st++) {
+    const int nx = stage_dims[2 * st], ny = stage_dims[2 * st + 1];
+    if (nx <= 0 || ny <= 0) continue;
+    dim3 grid((nx + 31) / 32, (ny + 7) / 8, n);
+    aug_stage_kernel<<<grid, 256, 0, s>>>(ops + (long long)st * n);
+  }
   SSP_CHECK_LAUNCH();
   return SSP_OK;
 }

@@ -259,4 +259,84 @@ int augment_sample_driver(Backend& be, const uint8_t* img, const uint8_t* mask, 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Batched execution (one launch per STAGE per batch instead of ~10 launches per sample).  A recording back end runs the very
+// same drivers as above for every sample and files the k-th call of a sample under stage k of an op table [stage][sample];
+// stages are then executed in order (the only dependencies are between consecutive calls of ONE sample), every op by
+// op_element() per element of its (nx, ny) extent -- on the GPU one thread per element with blockIdx.z = sample
+// (augment.cu), in the host harness plain loops.  The table holds device pointers and is copied with the batch's bytes.
+enum { OP_NONE = 0, OP_COEFFS = 1, OP_PASS = 2, OP_NEAREST = 3, OP_COMPOSITE = 4, OP_DISTORT = 5 };
+static constexpr int kMaxStages = 10;       // 2 x (2 coefficient tables + 2 passes) + composite + distort
+struct AugOp {
+  int kind, nx, ny, pad_;
+  PassArgs pass;                                                          // OP_PASS / OP_NEAREST
+  int in_size, in0, in1, out_size, resample, ksize; int* bounds; int* kk;  // OP_COEFFS
+  const uint8_t* img; const uint8_t* bg; const uint8_t* mask; const uint8_t* lut_pos; const uint8_t* lut_neg; uint8_t* comp_out;   // OP_COMPOSITE (nx = bytes per row)
+  const uint8_t* src; const uint8_t* luts; uint8_t* out_u8; float* out_chw;   // OP_DISTORT (nx x ny pixels)
+};
+SSP_HD void op_element(const AugOp& op, int x, int y) {
+  if (x >= op.nx || y >= op.ny) return;
+  switch (op.kind) {
+    case OP_COEFFS: coeff_row(op.in_size, op.in0, op.in1, op.out_size, op.resample, op.ksize, x, op.bounds + 2 * x, op.kk + (long long)x * op.ksize); break;
+    case OP_PASS: resample_pass_px(op.pass, x, y); break;
+    case OP_NEAREST: nearest_px(op.pass, x, y); break;
+    case OP_COMPOSITE: { const long long i = (long long)y * op.nx + x; op.comp_out[i] = composite_px(op.img[i], op.bg[i], op.mask[i], op.lut_pos, op.lut_neg); } break;
+    case OP_DISTORT: {
+      const long long n = (long long)op.nx * op.ny, i = (long long)y * op.nx + x;
+      uint8_t o[3];
+      distort_px(op.src + 3 * i, op.luts, op.luts + 256, op.luts + 512, o);
+      if (op.out_u8) { op.out_u8[3 * i] = o[0]; op.out_u8[3 * i + 1] = o[1]; op.out_u8[3 * i + 2] = o[2]; }
+      if (op.out_chw) { op.out_chw[i] = (float)o[0] / 255.0f; op.out_chw[n + i] = (float)o[1] / 255.0f; op.out_chw[2 * n + i] = (float)o[2] / 255.0f; }
+    } break;
+    default: break;
+  }
+}
+// records the calls of ONE sample into column `sample` of the table
+struct PlanBackend {
+  AugOp* table; int n_samples, sample, call; bool overflow;
+  AugOp* next() {
+    if (call >= kMaxStages) { overflow = true; return nullptr; }
+    AugOp* o = table + (long long)call * n_samples + sample;
+    call++;
+    return o;
+  }
+  void coeffs(int in_size, int in0, int in1, int out_size, int resample, int ksize, int* bounds, int* kk) {
+    if (AugOp* o = next()) { o->kind = OP_COEFFS; o->nx = out_size; o->ny = 1; o->in_size = in_size; o->in0 = in0; o->in1 = in1; o->out_size = out_size;
+                             o->resample = resample; o->ksize = ksize; o->bounds = bounds; o->kk = kk; }
+  }
+  void pass(const PassArgs& a) { if (AugOp* o = next()) { o->kind = OP_PASS; o->nx = a.dst_w; o->ny = a.dst_h; o->pass = a; } }
+  void nearest(const PassArgs& a) { if (AugOp* o = next()) { o->kind = OP_NEAREST; o->nx = a.dst_w; o->ny = a.dst_h; o->pass = a; } }
+  void composite(const uint8_t* img, const uint8_t* bg, const uint8_t* mask, const uint8_t* lp, const uint8_t* ln, long long n, uint8_t* out) {
+    if (AugOp* o = next()) { o->kind = OP_COMPOSITE; o->nx = row_bytes; o->ny = (int)(n / row_bytes); o->img = img; o->bg = bg; o->mask = mask;
+                             o->lut_pos = lp; o->lut_neg = ln; o->comp_out = out; }
+  }
+  void distort(const uint8_t* src, int w, int h, const uint8_t* luts, uint8_t* out_u8, float* out_chw) {
+    if (AugOp* o = next()) { o->kind = OP_DISTORT; o->nx = w; o->ny = h; o->src = src; o->luts = luts; o->out_u8 = out_u8; o->out_chw = out_chw; }
+  }
+  int row_bytes;      // 3 * ow of the sample being planned (composite is a flat byte op; rows give it a 2-D extent)
+};
+struct AugItem {      // one sample of a batch: the arguments of augment_sample_driver (device pointers)
+  const uint8_t* img; const uint8_t* mask; int ow, oh; const uint8_t* bg; int bw, bh; const uint8_t* luts; int pleft, ptop, cw, ch;
+  uint8_t* work; long long work_bytes; uint8_t* out_u8; float* out_chw;
+};
+// fills table[kMaxStages][n] (zeroed here) and stage_dims[kMaxStages][2] = largest (nx, ny) of every stage; 0 ok, < 0 error
+static inline int augment_batch_plan(const AugItem* items, int n, int out_w, int out_h, int resample, AugOp* table, int* stage_dims) {
+  for (long long i = 0; i < (long long)kMaxStages * n; i++) { AugOp z = AugOp(); table[i] = z; }
+  for (int s = 0; s < 2 * kMaxStages; s++) stage_dims[s] = 0;
+  for (int i = 0; i < n; i++) {
+    const AugItem& it = items[i];
+    PlanBackend be{table, n, i, 0, false, 3 * it.ow};
+    const int rc = augment_sample_driver(be, it.img, it.mask, it.ow, it.oh, it.bg, it.bw, it.bh, it.luts, it.pleft, it.ptop, it.cw, it.ch, out_w, out_h,
+                                         resample, it.work, it.work_bytes, it.out_u8, it.out_chw);
+    if (rc) return rc;
+    if (be.overflow) return -3;
+    for (int s = 0; s < be.call; s++) {
+      const AugOp& o = table[(long long)s * n + i];
+      if (o.nx > stage_dims[2 * s]) stage_dims[2 * s] = o.nx;
+      if (o.ny > stage_dims[2 * s + 1]) stage_dims[2 * s + 1] = o.ny;
+    }
+  }
+  return 0;
+}
+
 }  // namespace ssp_aug

@@ -17,6 +17,7 @@ BICUBIC on every Pillow since 7.0 (the default here) and NEAREST on the Pillow 5
 """
 from __future__ import annotations
 
+import os
 import random as _random
 
 import numpy as np
@@ -250,6 +251,13 @@ def _stage_fill(st, imgs, masks, bgs, params, offs):
     list(_POOL.map(one, jobs))
 
 
+class _AugItem(C.Structure):
+    """ssp_aug_item (include/ssp_b200.h)"""
+    _fields_ = [("img", C.c_void_p), ("mask", C.c_void_p), ("ow", C.c_int), ("oh", C.c_int), ("bg", C.c_void_p), ("bw", C.c_int), ("bh", C.c_int),
+                ("luts", C.c_void_p), ("pleft", C.c_int), ("ptop", C.c_int), ("cw", C.c_int), ("ch", C.c_int), ("work", C.c_void_p),
+                ("work_bytes", C.c_longlong), ("out_u8", C.c_void_p), ("out_chw", C.c_void_p)]
+
+
 class GpuAugmenter:
     """change_background + data_augmentation + ToTensor for a whole batch: one pinned staging buffer, ONE host->device copy,
     then the per-sample kernels on the current stream, writing straight into the (B,3,H,W) float32 network input.
@@ -261,8 +269,10 @@ class GpuAugmenter:
     imgs / masks / bgs: sequences of uint8 HxWx3 RGB arrays (or PIL images), what `Image.open(path).convert('RGB')` gives in
     load_data_detection (image.py:134-136).  `params` (optional argument) replays earlier draws instead of drawing."""
 
-    def __init__(self, device, resample=BICUBIC, keep_u8=False):
+    def __init__(self, device, resample=BICUBIC, keep_u8=False, batched=None):
         self.device = torch.device(device)
+        # one launch per pipeline stage for the whole batch (ssp_aug_batch_plan/run) instead of ~10 launches per sample
+        self.batched = (os.environ.get("SSP_AUG_BATCHED", "1") != "0") if batched is None else bool(batched)
         if self.device.type != "cuda":
             raise SspError("GpuAugmenter needs a CUDA device (no CPU fallback); got %s" % self.device)
         self.resample = resample
@@ -285,22 +295,43 @@ class GpuAugmenter:
         if params is None:
             params = [draw_augmentation(im.shape[1], im.shape[0], jitter, hue, saturation, exposure, rng) for im in imgs]
         offs, total, work_bytes = _stage_plan(imgs, masks, bgs, params, W, H, self.resample)
+        lib = load()
+        table_off = _a16(total)
+        table_bytes = int(lib.ssp_aug_batch_table_bytes(B)) if self.batched else 0
+        work_each = _a16(work_bytes)
+        work_total = work_each * (B if self.batched else 1)      # concurrent samples need their own scratch
+        total = table_off + table_bytes
         if self._stage is None or self._stage.numel() < total:
             self._stage = torch.empty(total, dtype=torch.uint8).pin_memory()
             self._dev = torch.empty(total, dtype=torch.uint8, device=self.device)
-        if self._work is None or self._work.numel() < work_bytes + 16:
-            self._work = _work(work_bytes, self.device)
+        if self._work is None or self._work.numel() < work_total + 16:
+            self._work = _work(work_total, self.device)
         if self._copied is not None:
             self._copied.synchronize()      # the previous batch's host->device copy has drained the pinned staging buffer
         _stage_fill(self._stage.numpy(), imgs, masks, bgs, params, offs)
+        out = torch.empty(B, 3, H, W, dtype=torch.float32, device=self.device)
+        u8 = torch.empty(B, H, W, 3, dtype=torch.uint8, device=self.device) if self.keep_u8 else None
+        base = self._dev.data_ptr()
+        if self.batched:
+            # the op table (device pointers, per-sample geometry) is planned on the host straight into the tail of the pinned
+            # staging buffer and travels in the batch's single host->device copy
+            items = (_AugItem * B)()
+            wbase = self._work.data_ptr()
+            for i, (im, bg, p, o) in enumerate(zip(imgs, bgs, params, offs)):
+                items[i] = _AugItem(base + o["img"], base + o["mask"], im.shape[1], im.shape[0], base + o["bg"], bg.shape[1], bg.shape[0],
+                                    base + o["luts"], p["pleft"], p["ptop"], p["cw"], p["ch"], wbase + i * work_each, work_each,
+                                    u8[i].data_ptr() if u8 is not None else None, out[i].data_ptr())
+            dims = (C.c_int * 20)()
+            call("ssp_aug_batch_plan", items, B, W, H, self.resample, C.c_void_p(self._stage.data_ptr() + table_off), table_bytes, dims)
         self._dev[:total].copy_(self._stage[:total], non_blocking=True)
         self._copied = torch.cuda.Event()
         self._copied.record()
         self.h2d_bytes = total
-        out = torch.empty(B, 3, H, W, dtype=torch.float32, device=self.device)
-        u8 = torch.empty(B, H, W, 3, dtype=torch.uint8, device=self.device) if self.keep_u8 else None
         s = stream_ptr()
-        base = self._dev.data_ptr()
+        if self.batched:
+            call("ssp_aug_batch_run", C.c_void_p(base + table_off), B, dims, s)
+            self.launches += sum(1 for k in range(10) if dims[2 * k] > 0)
+            return (out, params, u8) if self.keep_u8 else (out, params)
         for i, (im, bg, p, o) in enumerate(zip(imgs, bgs, params, offs)):
             call("ssp_aug_sample", C.c_void_p(base + o["img"]), C.c_void_p(base + o["mask"]), im.shape[1], im.shape[0],
                  C.c_void_p(base + o["bg"]), bg.shape[1], bg.shape[0], C.c_void_p(base + o["luts"]), p["pleft"], p["ptop"], p["cw"], p["ch"],

@@ -50,4 +50,17 @@ int h_augment_sample(const uint8_t* img, const uint8_t* mask, int ow, int oh, co
   HostBackend be;
   return augment_sample_driver(be, img, mask, ow, oh, bg, bw, bh, luts, pleft, ptop, cw, ch, out_w, out_h, resample, work, work_bytes, out_u8, out_chw);
 }
+// batched path: plan with the recording back end, then execute the op table stage by stage with plain loops
+long long h_aug_op_bytes() { return (long long)sizeof(AugOp); }
+long long h_aug_item_bytes() { return (long long)sizeof(AugItem); }
+int h_augment_batch(const AugItem* items, int n, int out_w, int out_h, int resample, AugOp* table, int* stage_dims) {
+  const int rc = augment_batch_plan(items, n, out_w, out_h, resample, table, stage_dims);
+  if (rc) return rc;
+  for (int s = 0; s < kMaxStages; s++)
+    for (int i = 0; i < n; i++) {
+      const AugOp& o = table[(long long)s * n + i];
+      for (int y = 0; y < o.ny; y++) for (int x = 0; x < o.nx; x++) op_element(o, x, y);
+    }
+  return 0;
+}
 }

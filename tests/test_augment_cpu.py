@@ -204,6 +204,47 @@ def test_staging_layout_feeds_the_kernel_core(host):
         I._stage_plan(imgs, [m[:10] for m in masks], bgs, params, W, H, I.BICUBIC)
 
 
+def test_batched_op_table_matches_per_sample_driver(host):
+    """the batched path (one launch per stage per batch): the recording back end + op_element() of augment_core.h, executed by the
+    host harness stage by stage over a mixed-size batch, produce the bytes of the oracle for every sample (uint8 and float32 CHW)"""
+    from singleshotpose_b200.image import _AugItem
+    host.h_aug_op_bytes.restype = C.c_longlong; host.h_aug_item_bytes.restype = C.c_longlong
+    assert host.h_aug_item_bytes() == C.sizeof(_AugItem)
+    sizes = [((160, 120), (100, 75)), ((96, 128), (64, 64)), ((200, 150), (333, 41)), ((160, 120), (160, 120)), ((64, 48), (20, 30)), ((104, 104), (104, 104))]
+    samples = [synth.photo_sample(30 + i, ow, oh, bw, bh) for i, ((ow, oh), (bw, bh)) in enumerate(sizes)]
+    imgs, masks, bgs = zip(*samples)
+    W = H = 104
+    rng = random.Random(200)
+    params = [I.draw_augmentation(im.shape[1], im.shape[0], 0.2, 0.1, 1.5, 1.5, rng) for im in imgs]
+    params[-1].update(pleft=0, ptop=0, cw=104, ch=104)            # same-size crop: Image.resize returns a copy (nearest op, fewer stages)
+    offs, total, work_bytes = I._stage_plan(imgs, masks, bgs, params, W, H, I.BICUBIC)
+    st = np.zeros(total, np.uint8)
+    I._stage_fill(st, imgs, masks, bgs, params, offs)
+    B = len(imgs)
+    each = (work_bytes + 15) & ~15
+    work = np.zeros(each * B + 16, np.uint8)
+    wbase = (work.ctypes.data + 15) & ~15
+    o8 = np.zeros((B, H, W, 3), np.uint8); of = np.zeros((B, 3, H, W), np.float32)
+    items = (_AugItem * B)()
+    base = st.ctypes.data
+    for i, (im, bg, p, o) in enumerate(zip(imgs, bgs, params, offs)):
+        items[i] = _AugItem(base + o["img"], base + o["mask"], im.shape[1], im.shape[0], base + o["bg"], bg.shape[1], bg.shape[0], base + o["luts"],
+                            p["pleft"], p["ptop"], p["cw"], p["ch"], wbase + i * each, each, o8[i].ctypes.data, of[i].ctypes.data)
+    table = np.zeros(10 * B * host.h_aug_op_bytes(), np.uint8)
+    dims = (C.c_int * 20)()
+    assert host.h_augment_batch(items, B, W, H, 3, _p(table), dims) == 0
+    assert sum(1 for k in range(10) if dims[2 * k] > 0) == 10 and max(dims) <= 3 * 200
+    rng = random.Random(200)
+    for i in range(B):
+        if i == B - 1:
+            want = A.distort_image(A.change_background(*samples[i]), params[i]["dhue"], params[i]["dsat"], params[i]["dexp"]) if hasattr(A, "distort_image") else None
+        else:
+            want = A.data_augmentation(A.change_background(*samples[i]), (W, H), 0.2, 0.1, 1.5, 1.5, rng=rng)[0]
+        if want is not None:
+            assert np.array_equal(o8[i], want), i
+        assert np.array_equal(of[i], (o8[i].transpose(2, 0, 1).astype(np.float32) / np.float32(255.0))), i
+
+
 def test_validation_batch_glue_with_oracle_resize():
     """load_validation_batch = per-image resize_u8 + to_tensor_u8; with both kernels swapped for the oracle (the GPU kernel itself is
     tested in test_gpu_augment.py) the stacking / dtype / layout glue is checked on the CPU"""

@@ -95,6 +95,12 @@ def test_augmenter_batch_mixed_sources_vs_oracle():
     # replaying recorded draws gives the same batch
     x2, _p, _u = aug(imgs, masks, bgs, (104, 104), params=params)
     assert torch.equal(x2, x)
+    # one launch per stage per batch (default) vs the per-sample launches: same bytes, an order of magnitude fewer launches
+    per_sample = I.GpuAugmenter("cuda", resample=rs, keep_u8=True, batched=False)
+    x3, _p, u3 = per_sample(imgs, masks, bgs, (104, 104), params=params)
+    assert aug.batched and torch.equal(x3, x) and torch.equal(u3, _u)
+    l0 = aug.launches; aug(imgs, masks, bgs, (104, 104), params=params)
+    assert aug.launches - l0 <= 10 < per_sample.launches
     with pytest.raises(ValueError):
         aug(imgs, masks[:2], bgs, (104, 104))
 
