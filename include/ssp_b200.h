@@ -68,14 +68,6 @@ int ssp_conv_gemm_bnact(int impl, const void* a_hi, const void* a_lo, long long 
                         const void* b_hi, const void* b_lo, int b_rows, int b_ld, int N, int H, int W, int taps, int cout,
                         const float* scale, const float* shift, float slope, void* d_hi, void* d_lo, int d_ld, int d_c0,
                         void* stream);
-/* ---- experimental (opt-in, SSP_FUSE_BNBWD=1): data gradient of a conv (autograd of darknet.py:156-160) whose epilogue also
- *      accumulates pass 1 of the BatchNorm backward of the PRODUCER that fed input channels [c_begin, c_end) through a direct
- *      route: S1 += sum dz, S2 += sum dz*xhat over valid rows, dz = dX * leaky'(y*scale+shift).  CTA-pair kernel only. ---- */
-int ssp_conv_gemm_dgrad_bnred(const void* dy, long long dy_rows, int dy_ld, int cout, const void* w_dgrad, int w_rows,
-                              int w_ld, int fmt, int N, int H, int W, int taps, int cin, float* dx, int dx_ld,
-                              long long dx_rows, const float* y_producer, int y_ld, const float* scale, const float* shift,
-                              const float* mean, const float* invstd, float slope, int c_begin, int c_end, double* s1,
-                              double* s2, void* stream);
 /* ---- first layer nn.Conv2d(3, 32, 3, 1, 1) (darknet.py:156, block 0): direct fp32 convolution of the NCHW image with the
  *      fp32 master weights [32][3][3][3] (k = (kh*3+kw)*3 + ci), output rows [row(n,h,w)][y_ld], optional fp64 BN statistics ---- */
 int ssp_conv0_direct(const float* x_nchw, const float* w, const float* bias_or_null, float* y, int y_ld,
@@ -113,9 +105,6 @@ int ssp_bias_grad_nchw(const float* g_nchw, float* dbias, int N, int C, int HW, 
 /* ---- parameters: weight re-pack from the fp32 master [cout][taps][cin]; optim.SGD (train.py:388) ---- */
 int ssp_pack_weights(const float* w, int cout, int taps, int cin, void* fwd_hi, void* fwd_lo, int fwd_ld,
                      void* dgrad, int dgrad_ld, int dgrad_fmt, void* stream);
-/* experimental shared-memory-tiled variant with identical outputs (opt-in, SSP_PACK=v2; see csrc/pack_v2.cu) */
-int ssp_pack_weights_v2(const float* w, int cout, int taps, int cin, void* fwd_hi, void* fwd_lo, int fwd_ld,
-                        void* dgrad, int dgrad_ld, int dgrad_fmt, void* stream);
 int ssp_sgd_step_flat(float* p, const float* g, float* v, long long n, float lr, float momentum,
                       float weight_decay, float grad_scale, void* stream);
 /* SGD and the operand-plane re-pack in ONE pass over the flat buffers (csrc/sgd_pack.cu).  `segments` is a DEVICE array with one

@@ -28,7 +28,6 @@ SIGNATURES = {
     "ssp_conv_gemm": [_i, _p, _p, _ll, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _ll, _i, _p, _p, _p, _p],
     "ssp_conv0_direct": [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _p],
     "ssp_conv_gemm_bnact": [_i, _p, _p, _ll, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _i, _i, _p],
-    "ssp_conv_gemm_dgrad_bnred": [_p, _ll, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _ll, _p, _i, _p, _p, _p, _p, _f, _i, _i, _p, _p, _p],
     "ssp_wgrad_gemm": [_i, _p, _ll, _i, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _f, _p],
     "ssp_bn_finalize": [_p, _p, _d, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _i, _p],
     "ssp_bn_apply": [_p, _i, _p, _p, _i, _i, _i, _i, _f, _p, _p, _i, _i, _i, _p, _p, _i, _i, _i, _p, _i, _p],
@@ -37,7 +36,6 @@ SIGNATURES = {
     "ssp_bn_bwd_finalize": [_p, _p, _p, _p, _i, _i, _f, _p],
     "ssp_bias_grad_nchw": [_p, _p, _i, _i, _i, _i, _f, _p],
     "ssp_pack_weights": [_p, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p],
-    "ssp_pack_weights_v2": [_p, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p],
     "ssp_sgd_step_flat": [_p, _p, _p, _ll, _f, _f, _f, _f, _p],
     "ssp_sgd_segment_blocks": [_i, _i, _i, _ll],
     "ssp_sgd_pack_step": [_p, _i, _i, _i, _p, _p, _p, _f, _f, _f, _f, _p],

@@ -16,7 +16,7 @@ int fail_msg(int code, const char* msg) { snprintf(g_err, sizeof(g_err), "%s", m
 int conv_gemm_tc(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
                  float*, int, long long, int, const float*, double*, double*, cudaStream_t, const FusedAct*);
 int conv_gemm_tc2(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
-                  float*, int, long long, int, const float*, double*, double*, cudaStream_t, const FusedAct*, const BnBwdFuse*);
+                  float*, int, long long, int, const float*, double*, double*, cudaStream_t, const FusedAct*);
 int conv_gemm_band(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
                    float*, int, long long, int, const float*, double*, double*, cudaStream_t);
 int conv_gemm_simt(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
@@ -38,7 +38,6 @@ int bn_bwd_apply(const float*, int, const float*, const float*, const float*, co
 int bn_bwd_finalize(double*, double*, float*, float*, int, int, float, cudaStream_t);
 int bias_grad_nchw(const float*, float*, int, int, int, int, float, cudaStream_t);
 int pack_weights(const float*, int, int, int, void*, void*, int, void*, int, int, cudaStream_t);
-int pack_weights_v2(const float*, int, int, int, void*, void*, int, void*, int, int, cudaStream_t);
 int sgd_step_flat(float*, const float*, float*, long long, float, float, float, float, cudaStream_t);
 int sgd_pack_step(const ssp_sgd_segment*, int, int, int, float*, const float*, float*, float, float, float, float, cudaStream_t);
 int region_loss_fwd_bwd(const float*, const float*, float*, double*, int, int, int, int, int, float, float, float, float, int, float, cudaStream_t);
@@ -87,7 +86,7 @@ int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo, long long a_rows
     if (rc != 1) return rc;          // 1 = layer not eligible (weights do not fit): per-tap kernel below
   }
   if (impl == SSP_IMPL_TC2)
-    return conv_gemm_tc2(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s), nullptr, nullptr);
+    return conv_gemm_tc2(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s), nullptr);
   return conv_gemm_tc(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s), nullptr);
 }
 int ssp_conv0_direct(const float* x, const float* w, const float* bias, float* y, int y_ld, double* ssum, double* ssq, int N, int H, int W, void* s) {
@@ -104,14 +103,6 @@ int ssp_conv_gemm_bnact(int impl, const void* a_hi, const void* a_lo, long long 
     return conv_gemm_tc(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, SSP_FMT_F16, SSP_FMT_F16, N, H, W, taps, cout, nullptr, 0, 0, EPI_BNACT,
                         nullptr, nullptr, nullptr, ST(s), &fa);
   return fail_msg(SSP_ERR_ARG, "ssp_conv_gemm_bnact: tensor-core implementations only");
-}
-int ssp_conv_gemm_dgrad_bnred(const void* dy, long long dy_rows, int dy_ld, int cout, const void* wd, int wd_rows, int wd_ld, int fmt, int N, int H,
-                              int W, int taps, int cin, float* dx, int dx_ld, long long dx_rows, const float* y, int y_ld, const float* scale,
-                              const float* shift, const float* mean, const float* invstd, float slope, int c_begin, int c_end, double* s1,
-                              double* s2, void* s) {
-  BnBwdFuse bw{y, y_ld, scale, shift, mean, invstd, slope, c_begin, c_end, s1, s2};
-  return conv_gemm_tc2(dy, nullptr, dy_rows, dy_ld, cout, wd, nullptr, wd_rows, wd_ld, fmt, fmt, N, H, W, taps, cin, dx, dx_ld, dx_rows, EPI_F32,
-                       nullptr, nullptr, nullptr, ST(s), nullptr, &bw);
 }
 int ssp_wgrad_gemm(int impl, const void* dy, long long dy_rows, int dy_ld, int cout, int dy_fmt, const void* x, long long x_rows, int x_ld,
                    int cin, int x_fmt, int N, int H, int W, int taps, float* dw, int dw_ld, int cin_store, float scale, void* s) {
@@ -143,9 +134,6 @@ int ssp_bn_bwd_apply(const float* y, int y_ld, const float* scale, const float* 
 }
 int ssp_bn_bwd_finalize(double* s1, double* s2, float* dgamma, float* dbeta, int C, int accumulate, float scale, void* s) { return bn_bwd_finalize(s1, s2, dgamma, dbeta, C, accumulate, scale, ST(s)); }
 int ssp_bias_grad_nchw(const float* g, float* db, int N, int C, int HW, int accumulate, float scale, void* s) { return bias_grad_nchw(g, db, N, C, HW, accumulate, scale, ST(s)); }
-int ssp_pack_weights_v2(const float* w, int cout, int taps, int cin, void* f_hi, void* f_lo, int ld_f, void* d, int ld_d, int d_fmt, void* s) {
-  return pack_weights_v2(w, cout, taps, cin, f_hi, f_lo, ld_f, d, ld_d, d_fmt, ST(s));
-}
 int ssp_pack_weights(const float* w, int cout, int taps, int cin, void* f_hi, void* f_lo, int ld_f, void* d, int ld_d, int d_fmt, void* s) {
   return pack_weights(w, cout, taps, cin, f_hi, f_lo, ld_f, d, ld_d, d_fmt, ST(s));
 }

@@ -50,7 +50,6 @@ struct ConvTc2Params {
   double* stat_sq;
   int epi;
   FusedAct fa;            // EPI_BNACT only
-  BnBwdFuse bw;           // MODE 2 only (experimental)
 };
 
 namespace {
@@ -96,8 +95,9 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-// MODE 0: training / generic epilogues.  MODE 1: the inference epilogue (EPI_BNACT).  MODE 2 (experimental, opt-in): EPI_F32
-// store + the BN-backward reduction of the producer layer (BnBwdFuse).  Separate instantiations keep MODE 0's code unchanged.
+// MODE 0: training / generic epilogues.  MODE 1: the inference epilogue (EPI_BNACT).  Separate instantiations keep MODE 0's
+// register budget.  (A MODE 2 that folded the BN-backward reduction of the producer into the data-gradient epilogue was measured
+// in round 2: 18.29 vs 18.13 ms/step, the extra Y reads sit on the dgrad critical path -- removed.)
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc2_kernel(const __grid_constant__ ConvTc2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc_pair(tmem_ptr, 512); tmem_relinquish_pair(); }
-  if (p.epi == EPI_STATS || MODE == 2)
+  if (p.epi == EPI_STATS)
     for (int i = threadIdx.x; i < 2 * kAccCols; i += kThreads) acc_sum[i] = 0.0;
   tc_fence_before();
   __syncthreads();
@@ -278,32 +278,6 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
             atomicAdd(&acc_sq[c0 + lane], (double)cq);
           }
         }
-        if constexpr (MODE == 2) {
-          // BN backward, pass 1, of the producer that fed input channels [c_begin, c_end): dz = dX * leaky'(z) over VALID rows
-          if (c0 >= p.bw.c_begin && c0 < p.bw.c_end) {
-            const int pc = c0 - p.bw.c_begin;
-            float g1[32], g2[32];
-            const float4* yrow = reinterpret_cast<const float4*>(p.bw.y + m * p.bw.y_ld + pc);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; j4++) {
-              float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (valid) yv = yrow[j4];                      // rows past the end of the map are never dereferenced
-              const float yy[4] = {yv.x, yv.y, yv.z, yv.w};
-#pragma unroll
-              for (int e = 0; e < 4; e++) {
-                const int j = j4 * 4 + e;
-                const float z = fmaf(yy[e], __ldg(p.bw.scale + pc + j), __ldg(p.bw.shift + pc + j));
-                const float dz = valid ? v[j] * (z > 0.f ? 1.f : p.bw.slope) : 0.f;
-                g1[j] = dz;
-                g2[j] = dz * ((yy[e] - __ldg(p.bw.mean + pc + j)) * __ldg(p.bw.invstd + pc + j));
-              }
-            }
-            const float cs = warp_transpose_sum32(g1, lane);
-            const float cq = warp_transpose_sum32(g2, lane);
-            atomicAdd(&acc_sum[pc + lane], (double)cs);
-            atomicAdd(&acc_sq[pc + lane], (double)cq);
-          }
-        }
       }
       tc_fence_before();
       __syncwarp();
@@ -314,13 +288,6 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
       for (int c = threadIdx.x - 128; c < p.cout; c += 128) {
         const double a = acc_sum[c], b = acc_sq[c];
         if (a != 0.0 || b != 0.0) { atomicAdd(p.stat_sum + c, a); atomicAdd(p.stat_sq + c, b); }
-      }
-    }
-    if constexpr (MODE == 2) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = threadIdx.x - 128; c < p.bw.c_end - p.bw.c_begin; c += 128) {
-        const double a = acc_sum[c], b = acc_sq[c];
-        if (a != 0.0 || b != 0.0) { atomicAdd(p.bw.s1 + c, a); atomicAdd(p.bw.s2 + c, b); }
       }
     }
   }
@@ -335,17 +302,11 @@ static int g_num_sms2 = 0;
 int conv_gemm_tc2(const void* a_hi, const void* a_lo, long long a_rows, int a_ld, int cin,
                  const void* b_hi, const void* b_lo, int b_rows, int b_ld, int a_fmt, int b_fmt,
                  int N, int H, int W, int taps, int cout, float* out, int out_ld, long long out_rows,
-                 int epi, const float* bias, double* stat_sum, double* stat_sq, cudaStream_t stream, const FusedAct* fa, const BnBwdFuse* bw) {
+                 int epi, const float* bias, double* stat_sum, double* stat_sq, cudaStream_t stream, const FusedAct* fa) {
   if (fa) {
     if (!fa->scale || !fa->shift || !fa->d_hi || !fa->d_lo || (cout % 32) || (fa->d_ld % 8) || (fa->d_c0 % 8))
       return fail_msg(SSP_ERR_ARG, "conv_gemm_tc2: fused BN+activation epilogue needs cout % 32 == 0 and 16-B aligned destination rows");
     epi = EPI_BNACT;
-  }
-  if (bw) {
-    if (fa || epi != EPI_F32 || !bw->y || !bw->scale || !bw->shift || !bw->mean || !bw->invstd || !bw->s1 || !bw->s2 || (bw->y_ld % 4) ||
-        ((uintptr_t)bw->y % 16) || (bw->c_begin % 32) || (bw->c_end % 32) || bw->c_begin < 0 || bw->c_end <= bw->c_begin ||
-        bw->c_end > cout || bw->c_end - bw->c_begin > kAccCols)
-      return fail_msg(SSP_ERR_ARG, "conv_gemm_tc2: bad BN-backward fusion argument (EPI_F32 only, 32-aligned channel range <= 1024 wide)");
   }
   if (!a_hi || !b_hi || (!out && !fa) || (taps != 1 && taps != 9) || cin <= 0 || cout <= 0) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc2: bad argument");
   if ((a_ld % 8) || (b_ld % 8)) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc2: leading dimensions must be multiples of 8 elements (16 B)");
@@ -387,7 +348,6 @@ int conv_gemm_tc2(const void* a_hi, const void* a_lo, long long a_rows, int a_ld
   p.stages = stages;
   p.out = out; p.out_ld = out_ld; p.bias = bias; p.stat_sum = stat_sum; p.stat_sq = stat_sq; p.epi = epi;
   if (fa) p.fa = *fa; else p.fa = FusedAct{nullptr, nullptr, 1.f, nullptr, nullptr, 0, 0};
-  if (bw) p.bw = *bw; else p.bw = BnBwdFuse{nullptr, 0, nullptr, nullptr, nullptr, nullptr, 1.f, 0, 0, nullptr, nullptr};
   int rc = 0;
   rc |= tmap_2d_16bit(&p.tmA[0], a_hi, (uint64_t)cin, (uint64_t)a_rows, (uint64_t)a_ld, 64, 128, a_fmt == FMT_BF16);
   rc |= tmap_2d_16bit(&p.tmB[0], b_hi, (uint64_t)taps * cin, (uint64_t)b_rows, (uint64_t)b_ld, 64, bn / 2, b_fmt == FMT_BF16);
@@ -401,14 +361,12 @@ int conv_gemm_tc2(const void* a_hi, const void* a_lo, long long a_rows, int a_ld
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, __FILE__, __LINE__);
     configured = 1;
   }
   const int total = p.m_tiles * p.n_tiles;
   int pairs = g_num_sms2 / 2; if (total < pairs) pairs = total;
   if (fa) conv_tc2_kernel<1><<<2 * pairs, kThreads, smem_bytes, stream>>>(p);
-  else if (bw) conv_tc2_kernel<2><<<2 * pairs, kThreads, smem_bytes, stream>>>(p);
   else conv_tc2_kernel<0><<<2 * pairs, kThreads, smem_bytes, stream>>>(p);     // __cluster_dims__(2,1,1): CTA pairs on one TPC
   SSP_CHECK_LAUNCH();
   return SSP_OK;

@@ -6,13 +6,14 @@
 // 8-B fp16 vectors), consecutive threads on consecutive channels -> fully coalesced rows.
 #include "ssp_common.cuh"
 
-// Occupancy knob for the HBM-bound BN kernels (97-118 registers -> 2 blocks/SM, 23 % warps active, 47-63 % of DRAM peak under
-// ncu): rebuilding with SSP_BN_MINBLOCKS=3 in the environment caps registers at 85 for a third block.  Undefined (default) = no cap.
-#ifdef SSP_BN_MINBLOCKS
-#define SSP_BN_BOUNDS __launch_bounds__(256, SSP_BN_MINBLOCKS)
-#else
-#define SSP_BN_BOUNDS __launch_bounds__(256)
+// Occupancy of the HBM-bound BN kernels: uncapped they use 97-118 registers -> 2 blocks/SM, 23 % warps active, 47-63 % of DRAM
+// peak under ncu (round 1).  Capped at 85 registers for a third resident block (a few spilled bytes per thread): same-box A/B
+// of the batch-64 step in round 2: 18.35 -> 17.92 ms (a fourth block, 64 registers, spills too much: 18.86 ms).
+// SSP_BN_MINBLOCKS=n python csrc/build.py rebuilds with another cap.
+#ifndef SSP_BN_MINBLOCKS
+#define SSP_BN_MINBLOCKS 3
 #endif
+#define SSP_BN_BOUNDS __launch_bounds__(256, SSP_BN_MINBLOCKS)
 
 namespace ssp {
 
@@ -475,23 +476,39 @@ __global__ void bias_grad_nchw_kernel(const float* __restrict__ g, float* __rest
 // Weight re-packing.  Master weights: fp32 [cout][taps][cin] (the memory behind the permuted nn.Conv2d.weight view).
 //   fwd  : hi/lo fp16 [cout][ld_f]      k = tap*cin + ci                 (B operand of the forward GEMM)
 //   dgrad: 16-bit     [cin][ld_d]       k = tap'*cout + co, tap' = taps-1-tap   (B operand of the data-gradient GEMM)
-__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int taps, int cin,
-                                    uint16_t* __restrict__ f_hi, uint16_t* __restrict__ f_lo, int ld_f,
-                                    uint16_t* __restrict__ d, int ld_d, int d_fmt) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)cout * taps * cin;
-  if (idx >= total) return;
-  const int ci = (int)(idx % cin);
-  const int tap = (int)((idx / cin) % taps);
-  const int co = (int)(idx / ((long long)cin * taps));
-  const float v = w[idx];
-  if (f_hi) {
-    uint16_t a, b; split_f16(v, a, b);
-    const long long o = (long long)co * ld_f + tap * cin + ci;
-    f_hi[o] = a; if (f_lo) f_lo[o] = b;
+// A 64(co) x 64(ci) tile of one tap per block moves through shared memory so that BOTH the forward planes and the transposed
+// data-gradient plane are written in 128-B rows (the one-thread-per-weight kernel of round 1 wrote the transposed plane with
+// row-strided 2-byte stores: 1.06 TB/s; outputs verified bit-identical on B200 before it was replaced).
+__global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const float* __restrict__ w, int cout, int taps, int cin,
+                                                                 uint16_t* __restrict__ f_hi, uint16_t* __restrict__ f_lo, int ld_f,
+                                                                 uint16_t* __restrict__ d, int ld_d, int d_fmt) {
+  __shared__ uint16_t tile[64][66];                 // [ci][co], +2 pad: 33-word row pitch, conflict-free both ways
+  const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64, tap = blockIdx.z;
+  const int lane64 = threadIdx.x & 63, grp = threadIdx.x >> 6;      // 4 groups of 64 threads
+#pragma unroll 4
+  for (int r = 0; r < 16; r++) {
+    const int co = co0 + r * 4 + grp, ci = ci0 + lane64;            // consecutive threads -> consecutive ci (coalesced fp32 reads)
+    uint16_t t = 0;
+    if (co < cout && ci < cin) {
+      const float v = w[((long long)co * taps + tap) * cin + ci];
+      if (f_hi) {
+        uint16_t a, b; split_f16(v, a, b);
+        const long long o = (long long)co * ld_f + tap * cin + ci;
+        f_hi[o] = a; if (f_lo) f_lo[o] = b;
+      }
+      t = cvt_f32_to_16(v, d_fmt);
+    }
+    tile[lane64][r * 4 + grp] = t;
   }
-  if (d) d[(long long)ci * ld_d + (long long)(taps - 1 - tap) * cout + co] = cvt_f32_to_16(v, d_fmt);
+  if (!d) return;
+  __syncthreads();
+#pragma unroll 4
+  for (int r = 0; r < 16; r++) {
+    const int ci = ci0 + r * 4 + grp, co = co0 + lane64;            // consecutive threads -> consecutive co (coalesced 16-bit writes)
+    if (ci < cin && co < cout) d[(long long)ci * ld_d + (long long)(taps - 1 - tap) * cout + co] = tile[r * 4 + grp][lane64];
+  }
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // optim.SGD(momentum, dampening=0, weight_decay) over one flat buffer (train.py:388):
@@ -637,9 +654,10 @@ int bias_grad_nchw(const float* g, float* db, int N, int C, int HW, int accumula
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
 int pack_weights(const float* w, int cout, int taps, int cin, void* f_hi, void* f_lo, int ld_f, void* d, int ld_d, int d_fmt, cudaStream_t s) {
-  if (!w) return fail_msg(SSP_ERR_ARG, "pack_weights: null pointer");
-  const long long total = (long long)cout * taps * cin;
-  pack_weights_kernel<<<nblk(total, 256), 256, 0, s>>>(w, cout, taps, cin, (uint16_t*)f_hi, (uint16_t*)f_lo, ld_f, (uint16_t*)d, ld_d, d_fmt);
+  if (!w || cout <= 0 || taps <= 0 || cin <= 0 || taps > 65535) return fail_msg(SSP_ERR_ARG, "pack_weights: bad argument");
+  dim3 grid((cin + 63) / 64, (cout + 63) / 64, taps);
+  if (grid.y > 65535) return fail_msg(SSP_ERR_ARG, "pack_weights: cout too large");
+  pack_weights_tiled_kernel<<<grid, 256, 0, s>>>(w, cout, taps, cin, (uint16_t*)f_hi, (uint16_t*)f_lo, ld_f, (uint16_t*)d, ld_d, d_fmt);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
 int sgd_step_flat(float* p, const float* g, float* v, long long n, float lr, float mu, float wd, float gscale, cudaStream_t s) {

@@ -15,96 +15,9 @@
 // The kernel is fp64-ALU / local-memory bound: ~1.6e4 flop per Jacobi sweep (6-9 sweeps), ~3e3 per LM evaluation, 120 B of HBM
 // traffic per problem.
 #include "ssp_common.cuh"
+#include "pnp_core.h"
 
 namespace ssp {
-
-#define PNP_MAXP 16
-
-struct Pose { double r[3], t[3]; };
-
-__device__ void rodrigues(const double r[3], double R[9], double* J /*27 or null: dR[k]/dr[i] at J[i*9+k]*/) {
-  const double th = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-  if (th < 2.220446049250313e-16) {
-    for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
-    if (J) {
-      for (int i = 0; i < 27; i++) J[i] = 0.0;
-      J[5] = -1; J[7] = 1; J[9 + 2] = 1; J[9 + 6] = -1; J[18 + 1] = -1; J[18 + 3] = 1;
-    }
-    return;
-  }
-  const double c = cos(th), s = sin(th), c1 = 1.0 - c, it = 1.0 / th;
-  const double u[3] = {r[0] * it, r[1] * it, r[2] * it};
-  const double rrt[9] = {u[0] * u[0], u[0] * u[1], u[0] * u[2], u[1] * u[0], u[1] * u[1], u[1] * u[2], u[2] * u[0], u[2] * u[1], u[2] * u[2]};
-  const double rx[9] = {0, -u[2], u[1], u[2], 0, -u[0], -u[1], u[0], 0};
-  for (int k = 0; k < 9; k++) R[k] = c * ((k % 4 == 0) ? 1.0 : 0.0) + c1 * rrt[k] + s * rx[k];
-  if (!J) return;
-  for (int i = 0; i < 3; i++) {
-    double drrt[9], drx[9];
-    for (int a = 0; a < 3; a++)
-      for (int b = 0; b < 3; b++) drrt[a * 3 + b] = (a == i ? u[b] : 0.0) + (b == i ? u[a] : 0.0);
-    for (int k = 0; k < 9; k++) drx[k] = 0.0;
-    if (i == 0) { drx[5] = -1; drx[7] = 1; } else if (i == 1) { drx[2] = 1; drx[6] = -1; } else { drx[1] = -1; drx[3] = 1; }
-    const double ri = u[i];
-    const double a0 = -s * ri, a1 = (s - 2 * c1 * it) * ri, a2 = c1 * it, a3 = (c - s * it) * ri, a4 = s * it;
-    for (int k = 0; k < 9; k++)
-      J[i * 9 + k] = a0 * ((k % 4 == 0) ? 1.0 : 0.0) + a1 * rrt[k] + a2 * drrt[k] + a3 * rx[k] + a4 * drx[k];
-  }
-}
-
-// cyclic Jacobi on a symmetric n x n matrix: A -> diag, V = eigenvectors (columns); returns the number of sweeps
-template <int n>
-__device__ int jacobi_eig(double A[n][n], double V[n][n]) {
-  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i][j] = (i == j) ? 1.0 : 0.0;
-  int sweep = 0;
-  for (; sweep < 30; sweep++) {
-    double off = 0.0, diag = 0.0;
-    for (int i = 0; i < n; i++) { diag += A[i][i] * A[i][i]; for (int j = i + 1; j < n; j++) off += A[i][j] * A[i][j]; }
-    if (off <= 1e-34 * diag || off == 0.0) break;
-    for (int p = 0; p < n - 1; p++)
-      for (int q = p + 1; q < n; q++) {
-        if (A[p][q] == 0.0) continue;
-        const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < n; k++) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
-        for (int k = 0; k < n; k++) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
-        for (int k = 0; k < n; k++) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
-      }
-  }
-  return sweep;
-}
-
-// in-place Cholesky solve of SPD n x n system (n <= 6); returns false if not positive definite
-template <int n>
-__device__ bool chol_solve(double A[n][n], double b[n]) {
-  for (int j = 0; j < n; j++) {
-    double d = A[j][j];
-    for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
-    if (!(d > 0.0)) return false;
-    d = sqrt(d); A[j][j] = d;
-    for (int i = j + 1; i < n; i++) {
-      double v = A[i][j];
-      for (int k = 0; k < j; k++) v -= A[i][k] * A[j][k];
-      A[i][j] = v / d;
-    }
-  }
-  for (int i = 0; i < n; i++) { double v = b[i]; for (int k = 0; k < i; k++) v -= A[i][k] * b[k]; b[i] = v / A[i][i]; }
-  for (int i = n - 1; i >= 0; i--) { double v = b[i]; for (int k = i + 1; k < n; k++) v -= A[k][i] * b[k]; b[i] = v / A[i][i]; }
-  return true;
-}
-
-__device__ double reproj_err(const double* M, const double* m, int np, const double p[6], double fx, double fy, double cx, double cy) {
-  double R[9]; rodrigues(p, R, nullptr);
-  double e = 0.0;
-  for (int i = 0; i < np; i++) {
-    const double X = M[3 * i], Y = M[3 * i + 1], Z = M[3 * i + 2];
-    const double x = R[0] * X + R[1] * Y + R[2] * Z + p[3], y = R[3] * X + R[4] * Y + R[5] * Z + p[4], z = R[6] * X + R[7] * Y + R[8] * Z + p[5];
-    const double iz = 1.0 / z;
-    const double du = fx * x * iz + cx - m[2 * i], dv = fy * y * iz + cy - m[2 * i + 1];
-    e += du * du + dv * dv;
-  }
-  return sqrt(e);
-}
 
 __global__ void __launch_bounds__(128) pnp_kernel(const float* __restrict__ P3, long long p3_stride, const float* __restrict__ uv,
                                                   const float* __restrict__ Kmat, int np, long long n, int max_iter,
@@ -112,128 +25,10 @@ __global__ void __launch_bounds__(128) pnp_kernel(const float* __restrict__ P3, 
                                                   int* __restrict__ work_out /*[n][3]: Jacobi sweeps, LM iterations, LM solves; or null*/) {
   const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n) return;
-  const double fx = Kmat[0], fy = Kmat[4], cx = Kmat[2], cy = Kmat[5];
-  double M[3 * PNP_MAXP], m[2 * PNP_MAXP];
-  const float* p3 = P3 + id * p3_stride;
-  const float* q = uv + id * 2 * np;
-  for (int i = 0; i < 3 * np; i++) M[i] = (double)p3[i];
-  for (int i = 0; i < 2 * np; i++) m[i] = (double)q[i];
-
-  // ---- DLT (cvFindExtrinsicCameraParams2, non-planar branch): smallest eigenvector of L^T L on the raw coordinates ----
-  double LL[12][12], LV[12][12];
-  for (int a = 0; a < 12; a++) for (int b = 0; b < 12; b++) LL[a][b] = 0.0;
-  for (int i = 0; i < np; i++) {
-    const double X[4] = {M[3 * i], M[3 * i + 1], M[3 * i + 2], 1.0};
-    const double x = (m[2 * i] - cx) / fx, y = (m[2 * i + 1] - cy) / fy, qq = x * x + y * y;
-    for (int a = 0; a < 4; a++)
-      for (int b = 0; b < 4; b++) {
-        const double xx = X[a] * X[b];
-        LL[a][b] += xx; LL[4 + a][4 + b] += xx;
-        LL[a][8 + b] -= x * xx; LL[4 + a][8 + b] -= y * xx;
-        LL[8 + a][8 + b] += qq * xx;
-      }
-  }
-  for (int a = 0; a < 8; a++) for (int b = 8; b < 12; b++) LL[b][a] = LL[a][b];
-  const int sweeps = jacobi_eig<12>(LL, LV);
-  int kmin = 0;
-  for (int k = 1; k < 12; k++) if (LL[k][k] < LL[kmin][kmin]) kmin = k;
-  double RR[9], tt[3];
-  for (int r = 0; r < 3; r++) {
-    RR[3 * r] = LV[4 * r][kmin]; RR[3 * r + 1] = LV[4 * r + 1][kmin]; RR[3 * r + 2] = LV[4 * r + 2][kmin];
-    tt[r] = LV[4 * r + 3][kmin];
-  }
-  const double det = RR[0] * (RR[4] * RR[8] - RR[5] * RR[7]) - RR[1] * (RR[3] * RR[8] - RR[5] * RR[6]) + RR[2] * (RR[3] * RR[7] - RR[4] * RR[6]);
-  if (det < 0) { for (int i = 0; i < 9; i++) RR[i] = -RR[i]; for (int i = 0; i < 3; i++) tt[i] = -tt[i]; }
-  double sc = 0; for (int i = 0; i < 9; i++) sc += RR[i] * RR[i];
-  sc = sqrt(sc);
-  // polar decomposition: R = RR (RR^T RR)^(-1/2)
-  double G[3][3], Vg[3][3];
-  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { double v = 0; for (int k = 0; k < 3; k++) v += RR[3 * k + a] * RR[3 * k + b]; G[a][b] = v; }
-  jacobi_eig<3>(G, Vg);
-  double Gi[3][3];
-  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { double v = 0; for (int k = 0; k < 3; k++) v += Vg[a][k] * Vg[b][k] / sqrt(fmax(G[k][k], 1e-300)); Gi[a][b] = v; }
-  double R0[9];
-  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { double v = 0; for (int k = 0; k < 3; k++) v += RR[3 * a + k] * Gi[k][b]; R0[3 * a + b] = v; }
-  double p[6];
-  { const double f = sqrt(3.0) / sc; p[3] = tt[0] * f; p[4] = tt[1] * f; p[5] = tt[2] * f; }
-  {  // rotation matrix -> axis-angle (cv2.Rodrigues inverse branch structure)
-    const double rv[3] = {R0[7] - R0[5], R0[2] - R0[6], R0[3] - R0[1]};
-    const double s = sqrt((rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]) * 0.25);
-    double c = (R0[0] + R0[4] + R0[8] - 1.0) * 0.5; c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
-    const double th = acos(c);
-    if (s < 1e-5) {
-      if (c > 0) { p[0] = p[1] = p[2] = 0.0; }
-      else {
-        double tx = sqrt(fmax((R0[0] + 1) * 0.5, 0.0));
-        double ty = sqrt(fmax((R0[4] + 1) * 0.5, 0.0)) * (R0[1] < 0 ? -1.0 : 1.0);
-        double tz = sqrt(fmax((R0[8] + 1) * 0.5, 0.0)) * (R0[2] < 0 ? -1.0 : 1.0);
-        if (fabs(tx) < fabs(ty) && fabs(tx) < fabs(tz) && ((R0[5] > 0) != (ty * tz > 0))) tz = -tz;
-        const double nn = th / sqrt(tx * tx + ty * ty + tz * tz);
-        p[0] = tx * nn; p[1] = ty * nn; p[2] = tz * nn;
-      }
-    } else {
-      const double f = 0.5 / s * th;
-      p[0] = rv[0] * f; p[1] = rv[1] * f; p[2] = rv[2] * f;
-    }
-  }
-
-  // ---- Levenberg-Marquardt (CvLevMarq schedule) ----
-  int lam_lg10 = -3, iters = 0, solves = 0;
-  double prev_err = 0.0, e = 0.0;
-  while (true) {
-    double R[9], dR[27];
-    rodrigues(p, R, dR);
-    double JtJ[6][6] = {}, Jte[6] = {};
-    double err2 = 0.0;
-    for (int i = 0; i < np; i++) {
-      const double X = M[3 * i], Y = M[3 * i + 1], Z = M[3 * i + 2];
-      const double x = R[0] * X + R[1] * Y + R[2] * Z + p[3], y = R[3] * X + R[4] * Y + R[5] * Z + p[4], z = R[6] * X + R[7] * Y + R[8] * Z + p[5];
-      const double iz = 1.0 / z, xn = x * iz, yn = y * iz;
-      const double eu = fx * xn + cx - m[2 * i], ev = fy * yn + cy - m[2 * i + 1];
-      err2 += eu * eu + ev * ev;
-      double ju[6], jv[6];
-      for (int j = 0; j < 3; j++) {
-        const double* d = dR + 9 * j;
-        const double dx = d[0] * X + d[1] * Y + d[2] * Z, dy = d[3] * X + d[4] * Y + d[5] * Z, dz = d[6] * X + d[7] * Y + d[8] * Z;
-        ju[j] = fx * (dx - xn * dz) * iz; jv[j] = fy * (dy - yn * dz) * iz;
-      }
-      ju[3] = fx * iz; ju[4] = 0.0; ju[5] = -fx * xn * iz;
-      jv[3] = 0.0; jv[4] = fy * iz; jv[5] = -fy * yn * iz;
-      for (int a = 0; a < 6; a++) {
-        Jte[a] += ju[a] * eu + jv[a] * ev;
-        for (int b = a; b < 6; b++) JtJ[a][b] += ju[a] * ju[b] + jv[a] * jv[b];
-      }
-    }
-    for (int a = 0; a < 6; a++) for (int b = 0; b < a; b++) JtJ[a][b] = JtJ[b][a];
-    if (iters == 0) prev_err = sqrt(err2);
-    double prev[6];
-    for (int a = 0; a < 6; a++) prev[a] = p[a];
-    bool first = true;
-    while (true) {
-      if (!first) { if (++lam_lg10 > 16) break; }
-      first = false;
-      const double lam = exp(lam_lg10 * 2.302585092994046);
-      double A[6][6], d[6];
-      for (int a = 0; a < 6; a++) { for (int b = 0; b < 6; b++) A[a][b] = JtJ[a][b]; A[a][a] *= 1.0 + lam; d[a] = Jte[a]; }
-      if (!chol_solve<6>(A, d)) { for (int a = 0; a < 6; a++) d[a] = 0.0; }
-      solves++;
-      for (int a = 0; a < 6; a++) p[a] = prev[a] - d[a];
-      e = reproj_err(M, m, np, p, fx, fy, cx, cy);
-      if (!(e > prev_err)) break;
-    }
-    lam_lg10 = lam_lg10 - 1 < -16 ? -16 : lam_lg10 - 1;
-    iters++;
-    double dn = 0, pn = 0;
-    for (int a = 0; a < 6; a++) { dn += (p[a] - prev[a]) * (p[a] - prev[a]); pn += prev[a] * prev[a]; }
-    if (iters >= max_iter || sqrt(dn) < 1.1920929e-07 * sqrt(pn)) break;
-    prev_err = e;
-  }
-  double R[9];
-  rodrigues(p, R, nullptr);
-  for (int i = 0; i < 9; i++) R_out[id * 9 + i] = R[i];
-  for (int i = 0; i < 3; i++) t_out[id * 3 + i] = p[3 + i];
-  if (iters_out) iters_out[id] = iters;
-  if (work_out) { work_out[3 * id] = sweeps; work_out[3 * id + 1] = iters; work_out[3 * id + 2] = solves; }
+  int work[3];
+  ssp_pnp::pnp_solve_one(P3 + id * p3_stride, uv + id * 2 * np, Kmat, np, max_iter, R_out + id * 9, t_out + id * 3, work);
+  if (iters_out) iters_out[id] = work[1];
+  if (work_out) { work_out[3 * id] = work[0]; work_out[3 * id + 1] = work[1]; work_out[3 * id + 2] = work[2]; }
 }
 
 // compute_projection (utils.py:40-45): uv = K [R|t] X / z for every vertex; fp64 math, fp32 result [n][2][nv]

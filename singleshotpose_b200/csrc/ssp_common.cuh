@@ -34,16 +34,6 @@ struct FusedAct {
   const float* scale; const float* shift; float slope;
   uint16_t* d_hi; uint16_t* d_lo; long long d_ld; int d_c0;
 };
-// experimental (opt-in) fusion of bn_bwd_reduce into the data-gradient GEMM of the consumer layer: for the output columns
-// [c_begin, c_end) -- the input channels this conv received from ONE batch-normalised producer through a direct route -- the
-// epilogue also accumulates S1 = sum dz, S2 = sum dz * xhat of that producer (dz = dX * leaky'(z), z = y*scale+shift).
-struct BnBwdFuse {
-  const float* y; long long y_ld;                 // producer's conv output, same padded-flat rows as dX
-  const float* scale; const float* shift; const float* mean; const float* invstd;
-  float slope; int c_begin, c_end;
-  double* s1; double* s2;
-};
-
 struct Geom {
   int N, H, W;
   __host__ __device__ int Wp() const { return W + 1; }

@@ -171,11 +171,11 @@ class Engine:
         self.tc2_min_n = int(os.environ.get("SSP_TC2_MIN_N", "128"))
         self.use_band = os.environ.get("SSP_BAND", "1") != "0"
         self.fuse_eval = os.environ.get("SSP_FUSE_EVAL", "1") != "0"
-        # "v2": experimental shared-memory-tiled weight re-pack (csrc/pack_v2.cu), opt-in until measured on hardware
-        self.pack_fn = "ssp_pack_weights_v2" if os.environ.get("SSP_PACK", "v1").lower() == "v2" else "ssp_pack_weights"
-        wimpl = os.environ.get("SSP_WGRAD_IMPL", "simt" if impl == "simt" else "tc").lower()
-        # "tc2": experimental CTA-pair weight-gradient kernel (csrc/wgrad_tc2.cu), opt-in until measured on hardware
-        self.wgrad_impl = {"simt": _lib.IMPL_SIMT, "tc2": _lib.IMPL_TC2}.get(wimpl, _lib.IMPL_TC)
+        self.pack_fn = "ssp_pack_weights"
+        wimpl = os.environ.get("SSP_WGRAD_IMPL", "simt" if impl == "simt" else "tc2").lower()
+        # "tc2" (default): CTA-pair weight-gradient kernel (csrc/wgrad_tc2.cu) where cout and cin are multiples of 256, the 1-CTA
+        # kernel elsewhere (the ABI falls back by itself); same-box A/B at batch 64: wgrad 4.0 -> 3.5 ms/step, step -0.35 ms
+        self.wgrad_impl = {"simt": _lib.IMPL_SIMT, "tc": _lib.IMPL_TC}.get(wimpl, _lib.IMPL_TC2)
         # backward operands: one 16-bit format for dY, W and X (tcgen05 kind::f16 cannot mix fp16 with bf16 -- illegal
         # instruction, measured).  fp16 + a static loss scale (saturating conversion) is 8x more precise than bf16.
         # The activation planes are fp16, so dY and the dgrad weights are fp16 too.
@@ -185,14 +185,7 @@ class Engine:
         self.fast = os.environ.get("SSP_PRECISION", "parity").lower() == "fast"   # single-term forward (no hi/lo)
         self.launches = 0
         self.overlap = os.environ.get("SSP_OVERLAP", "1") != "0"
-        # experimental (opt-in, not yet measured): the BN-backward reduction of a producer with ONE direct consumer runs in the
-        # epilogue of that consumer's data-gradient GEMM (csrc/conv_tc2.cu MODE 2) instead of as its own pass over Y and dX
-        self.fuse_bnbwd = os.environ.get("SSP_FUSE_BNBWD", "0") == "1"
         self.compact_pool_reduce = os.environ.get("SSP_POOL_REDUCE", "compact") != "full"
-        self._direct_producer = {}
-        for Lp in self.layers:
-            if Lp.bn and len(Lp.dests) == 1 and Lp.dests[0][2] == _lib.ROUTE_DIRECT and Lp.cout % 32 == 0 and Lp.cout <= 1024 and Lp.dests[0][1] % 32 == 0:
-                self._direct_producer.setdefault(Lp.dests[0][0], (Lp.index, Lp.dests[0][1]))
         self._side = None
         self.grad_ready_hook = None  # fn(first layer index, stream): every gradient of layers >= that index is complete in `stream` order
         self.profile = None          # set to [] to record (kind, layer block, algorithmic flops, start event, end event) per GEMM launch
@@ -486,7 +479,6 @@ class Engine:
         else:
             ws, wstream = s, None
         inv = 1.0 / self.grad_scale        # the whole backward chain carries the loss scale; undone where grads are written
-        reduced_in_dgrad = set()           # producers whose S1/S2 were accumulated by their consumer's dgrad epilogue (experimental)
         for L in reversed(self.layers):
             i = L.index
             conv, bn = mods[i]
@@ -502,9 +494,7 @@ class Engine:
                 common = [ptr(B.y[i]), B.y[i].shape[1], ptr(st["scale"]), ptr(st["shift"]), ptr(st["mean"]), ptr(st["invstd"]),
                           ptr(bn.weight.data), N, L.cout, h, w, L.slope, *srcs, ptr(st["s1"]), ptr(st["s2"])]
                 yp = B.ypool[i]
-                if i in reduced_in_dgrad:
-                    pass
-                elif yp is not None:
+                if yp is not None:
                     # pooled consumer(s): only the arg-max position of a 2x2 window receives gradient, so S1 / S2 are sums over
                     # pooled cells -- reduce at a quarter of the resolution from the arg-max plane; S1 / S2 are linear in the
                     # upstream gradient, so any other consumer (layer 16 also feeds the reorg branch) adds its own pass
@@ -536,19 +526,9 @@ class Engine:
                 ev.record(main)                      # dY of this layer is complete
             if not L.first:                          # data gradient first: it is on the critical path of the next layer
                 wd = self.w_d[i]
-                prod = self._direct_producer.get(i) if self.fuse_bnbwd and self._conv_impl(L.cin, L.taps) == _lib.IMPL_TC2 else None
-                if prod is not None:
-                    j, c0 = prod
-                    Lj, stj = self.layers[j], B.stat[j]
-                    self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm_dgrad_bnred", ptr(dy), B.rows[i], dy.shape[1], L.cout, ptr(wd), L.cin, wd.shape[1],
-                               self.grad_fmt, N, h, w, L.taps, L.cin, ptr(B.dx[i]), B.dx[i].shape[1], B.rows[i], ptr(B.y[j]), B.y[j].shape[1],
-                               ptr(stj["scale"]), ptr(stj["shift"]), ptr(stj["mean"]), ptr(stj["invstd"]), Lj.slope, c0, c0 + Lj.cout,
-                               ptr(stj["s1"]), ptr(stj["s2"]), s)
-                    reduced_in_dgrad.add(j)
-                else:
-                    self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cin, L.taps), ptr(dy), None, B.rows[i], dy.shape[1], L.cout,
-                               ptr(wd), None, L.cin, wd.shape[1], self.grad_fmt, self.grad_fmt, N, h, w, L.taps, L.cin, ptr(B.dx[i]),
-                               B.dx[i].shape[1], B.rows[i], _lib.EPI_F32, None, None, None, s)
+                self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cin, L.taps), ptr(dy), None, B.rows[i], dy.shape[1], L.cout,
+                           ptr(wd), None, L.cin, wd.shape[1], self.grad_fmt, self.grad_fmt, N, h, w, L.taps, L.cin, ptr(B.dx[i]),
+                           B.dx[i].shape[1], B.rows[i], _lib.EPI_F32, None, None, None, s)
             if overlap:
                 side.wait_event(ev)
             if L.first:

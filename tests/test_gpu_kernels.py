@@ -201,9 +201,8 @@ def test_dgrad_vs_unquantised_fp64(case):
     assert l2 > 5e-5
 
 
-@pytest.mark.skipif(os.environ.get("SSP_EXPERIMENTAL", "0") != "1", reason="experimental CTA-pair wgrad (csrc/wgrad_tc2.cu): opt-in, SSP_EXPERIMENTAL=1")
 @pytest.mark.parametrize("case", [(2, 13, 13, 256, 256, 3), (1, 13, 13, 512, 256, 1), (2, 26, 26, 256, 512, 3), (64, 13, 13, 512, 256, 3)])
-def test_wgrad_pair_experimental(case):
+def test_wgrad_pair_matches_single_cta_and_torch(case):
     """CTA-pair weight gradient vs the 1-CTA tensor-core kernel and torch (eligible shapes: cout, cin multiples of 256)"""
     N, H, W, cin, cout, k = case
     g = torch.Generator().manual_seed(11)
@@ -223,24 +222,6 @@ def test_wgrad_pair_experimental(case):
         ref = torch.nn.grad.conv2d_weight(x.half().double(), (cout, cin, k, k), dy.half().double(), padding=(k - 1) // 2).float()
         out = outs[1].view(cout, k, k, cin).permute(0, 3, 1, 2).cpu()
         assert (out - ref).abs().max() / ref.abs().max() < 1e-4
-
-
-@pytest.mark.skipif(os.environ.get("SSP_EXPERIMENTAL", "0") != "1", reason="experimental tiled weight re-pack (csrc/pack_v2.cu): opt-in, SSP_EXPERIMENTAL=1")
-@pytest.mark.parametrize("shape", [(64, 9, 32), (1024, 9, 512), (20, 1, 1024), (64, 1, 512), (1024, 9, 1280), (32, 1, 27), (130, 9, 70)])
-def test_pack_weights_v2_experimental(shape):
-    """the tiled re-pack writes exactly the bytes of the default kernel (forward hi/lo planes and the transposed dgrad copy)"""
-    cout, taps, cin = shape
-    w = torch.randn(cout, taps, cin, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
-    ld_f, ld_d = (taps * cin + 7) // 8 * 8, (taps * cout + 7) // 8 * 8
-    outs = []
-    for fn in ("ssp_pack_weights", "ssp_pack_weights_v2"):
-        hi = torch.zeros(cout, ld_f, dtype=torch.float16, device=DEV); lo = torch.zeros_like(hi)
-        d = torch.zeros(cin, ld_d, dtype=torch.float16, device=DEV)
-        call(fn, ptr(w), cout, taps, cin, ptr(hi), ptr(lo), ld_f, ptr(d), ld_d, _lib.FMT_F16, stream_ptr())
-        torch.cuda.synchronize()
-        outs.append((hi, lo, d))
-    for a, b in zip(*outs):
-        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
 
 
 def _bn_ref(y, gamma, beta, route):
