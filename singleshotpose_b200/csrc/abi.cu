@@ -98,7 +98,7 @@ int ssp_conv_gemm_bnact(int impl, const void* a_hi, const void* a_lo, long long 
   FusedAct fa{scale, shift, slope, (uint16_t*)d_hi, (uint16_t*)d_lo, d_ld, d_c0};
   if (impl == SSP_IMPL_TC2)
     return conv_gemm_tc2(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, SSP_FMT_F16, SSP_FMT_F16, N, H, W, taps, cout, nullptr, 0, 0, EPI_BNACT,
-                         nullptr, nullptr, nullptr, ST(s), &fa, nullptr);
+                         nullptr, nullptr, nullptr, ST(s), &fa);
   if (impl == SSP_IMPL_TC || impl == SSP_IMPL_BAND)
     return conv_gemm_tc(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, SSP_FMT_F16, SSP_FMT_F16, N, H, W, taps, cout, nullptr, 0, 0, EPI_BNACT,
                         nullptr, nullptr, nullptr, ST(s), &fa);

@@ -28,6 +28,7 @@
 //   warps 4-7 epilogue                     tcgen05.ld -> registers -> (bias | BN statistics) -> global fp32
 #include "ssp_common.cuh"
 #include "tmap.cuh"
+#include <stdlib.h>
 
 namespace ssp {
 
@@ -37,6 +38,7 @@ struct ConvTc2Params {
   long long m_rows;       // rows of the output matrix that exist (N*(H+1)*(W+1))
   long long store_rows;   // rows that may be written (allocation bound)
   int m_tiles, n_tiles;
+  int ksplit;             // > 1: every tile's K loop is cut into ksplit work items whose partial sums meet in `out` through fp32 atomics (EPI_F32 only)
   int kc_per_tap, cin, taps;
   int shifts[9];
   int Wp, HpWp;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;      // m_tiles counts 256-row pair tiles
+  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;      // work items; m_tiles counts 256-row pair tiles
   const uint32_t rank = cluster_ctarank();
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const int kblocks = p.taps * p.kc_per_tap;
@@ -143,12 +145,15 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx = 2u * (uint32_t)(p.n_terms == 3 ? 2 : 1) * (uint32_t)(kABytes + p.b_bytes);   // both CTAs' bytes
-      for (int t = cid; t < total_tiles; t += ncl) {
+      for (int w = cid; w < total_tiles; w += ncl) {
+        const int t = w / p.ksplit, ks = w - t * p.ksplit;
         const int mt = t / p.n_tiles, nt = t % p.n_tiles;
         const int m0 = mt * 256 + (int)rank * 128, n0 = nt * p.bn + (int)rank * (p.bn / 2);
-        for (int tap = 0; tap < p.taps; tap++) {
-          const int arow = m0 + p.shifts[tap];
-          for (int kc = 0; kc < p.kc_per_tap; kc++) {
+        const int kb0 = ks * kblocks / p.ksplit, kb1 = (ks + 1) * kblocks / p.ksplit;
+        {
+          for (int kb = kb0; kb < kb1; kb++) {
+            const int tap = kb / p.kc_per_tap, kc = kb - tap * p.kc_per_tap;
+            const int arow = m0 + p.shifts[tap];
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = stage_base + (size_t)stage * p.stage_bytes;
             if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
@@ -171,13 +176,15 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
     if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int t = cid; t < total_tiles; t += ncl, it++) {
+      for (int w = cid; w < total_tiles; w += ncl, it++) {
         const int buf = it & 1;
         mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.bn);
         uint32_t acc = 0;
-        for (int kb = 0; kb < kblocks; kb++) {
+        const int ks = w % p.ksplit;
+        const int nkb = (ks + 1) * kblocks / p.ksplit - ks * kblocks / p.ksplit;
+        for (int kb = 0; kb < nkb; kb++) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + (size_t)stage * p.stage_bytes);
@@ -206,8 +213,9 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
     // ------------------------------------------------------------------ epilogue (128 threads = 128 TMEM lanes)
     const int q = warp - 4;
     int it = 0;
-    for (int t = cid; t < total_tiles; t += ncl, it++) {
+    for (int w = cid; w < total_tiles; w += ncl, it++) {
       const int buf = it & 1;
+      const int t = w / p.ksplit;
       const int mt = t / p.n_tiles, nt = t % p.n_tiles;
       const long long m = (long long)mt * 256 + rank * 128 + q * 32 + lane;
       const int n0 = nt * p.bn;
@@ -257,7 +265,16 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
 #pragma unroll
           for (int j = 0; j < 32; j++) if (c0 + j < p.cout) v[j] += __ldg(p.bias + c0 + j);
         }
-        if (can_store) {
+        if (can_store && p.ksplit > 1) {            // split K: partial sums of the ksplit work items meet in the (pre-zeroed) output
+          if (c0 + 32 <= p.cout) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              atomicAdd(reinterpret_cast<float4*>(orow + c0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) if (c0 + j < p.cout) atomicAdd(orow + c0 + j, v[j]);
+          }
+        } else if (can_store) {
           if (c0 + 32 <= p.cout) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -364,7 +381,26 @@ int conv_gemm_tc2(const void* a_hi, const void* a_lo, long long a_rows, int a_ld
     if (e != cudaSuccess) return fail_cuda(e, __FILE__, __LINE__);
     configured = 1;
   }
-  const int total = p.m_tiles * p.n_tiles;
+  // Wave quantisation: the 13x13 / 26x26 maps give 49 / 183 pair tiles per N tile, i.e. 98 ... 245 tiles for 74 CTA pairs (66 ... 88 %
+  // of the last wave busy).  For the plain-store epilogue (data gradient) the K loop is cut so that tiles x ksplit fills whole waves;
+  // the partial sums are added with fp32 vector atomics into the zeroed output.  (49 x 3 = 147 ~ 2 x 74: three cuts fit almost exactly.)
+  p.ksplit = 1;
+  static const int splitk_on = []() { const char* e = getenv("SSP_DGRAD_SPLITK"); return e ? atoi(e) : 0; }();
+  if (splitk_on && epi == EPI_F32 && !fa && out) {
+    const int npairs = g_num_sms2 / 2, tiles = p.m_tiles * p.n_tiles, kb = taps * p.kc_per_tap;
+    double best = (double)tiles / ((double)((tiles + npairs - 1) / npairs) * npairs);
+    for (int sp = 2; sp <= 4; sp++) {
+      if (kb / sp < 8) break;                                  // keep >= 8 k-blocks (512 K elements) per item
+      const int items = tiles * sp;
+      const double eff = (double)items / ((double)((items + npairs - 1) / npairs) * npairs) - 0.03 * (sp - 1);   // atomics are not free
+      if (eff > best + 0.05) { best = eff; p.ksplit = sp; }
+    }
+    if (p.ksplit > 1) {
+      cudaError_t e = cudaMemsetAsync(out, 0, (size_t)out_rows * out_ld * sizeof(float), stream);
+      if (e != cudaSuccess) return fail_cuda(e, __FILE__, __LINE__);
+    }
+  }
+  const int total = p.m_tiles * p.n_tiles * p.ksplit;
   int pairs = g_num_sms2 / 2; if (total < pairs) pairs = total;
   if (fa) conv_tc2_kernel<1><<<2 * pairs, kThreads, smem_bytes, stream>>>(p);
   else conv_tc2_kernel<0><<<2 * pairs, kThreads, smem_bytes, stream>>>(p);     // __cluster_dims__(2,1,1): CTA pairs on one TPC
