@@ -49,16 +49,82 @@ SSP_HD void rodrigues(const double r[3], double R[9], double* J /*27 or null: dR
   }
 }
 
-// cyclic Jacobi on a symmetric n x n matrix: A -> diag, V = eigenvectors (columns); returns the number of sweeps
+// cyclic Jacobi on a symmetric n x n matrix: A -> diag, V = eigenvectors (columns); returns the number of sweeps.
+// Works on the upper triangle only, each rotation through scalar temporaries (the textbook form: the pivot is set to zero and
+// the diagonal updated by t*a_pq exactly, symmetry cannot drift), loops kept rolled.  Round 2, B200: the two-sided form that
+// rotated whole columns and then whole rows in place (jacobi_eig_twosided below, kept for the probe) is right on the host and at
+// nvcc -O0 but does NOT converge as device code at -O3 for n = 12 (tools/probes/pnp_probe.cu: 128 of 128 problems wrong,
+// negative "eigenvalues" of a PSD matrix; -fmad=false makes no difference) -- nvcc unrolls the outer pivot loop and re-orders the
+// overlapping column / row updates.
+#ifndef PNP_JACOBI_VARIANT
+#define PNP_JACOBI_VARIANT 2
+#endif
+#if defined(__CUDACC__)
+#define PNP_ROLLED _Pragma("unroll 1")
+#else
+#define PNP_ROLLED
+#endif
 template <int n>
-SSP_HD int jacobi_eig(double A[n][n], double V[n][n]) {
+SSP_HD int jacobi_eig_upper(double A[n][n], double V[n][n]) {
+  PNP_ROLLED
+  for (int i = 0; i < n; i++) {
+    PNP_ROLLED
+    for (int j = 0; j < n; j++) V[i][j] = (i == j) ? 1.0 : 0.0;
+  }
+  int sweep = 0;
+  PNP_ROLLED
+  for (; sweep < 30; sweep++) {
+    double off = 0.0, diag = 0.0;
+    PNP_ROLLED
+    for (int i = 0; i < n; i++) {
+      diag += A[i][i] * A[i][i];
+      PNP_ROLLED
+      for (int j = i + 1; j < n; j++) off += A[i][j] * A[i][j];
+    }
+    if (off <= 1e-34 * diag || off == 0.0) break;
+    PNP_ROLLED
+    for (int p = 0; p < n - 1; p++) {
+      PNP_ROLLED
+      for (int q = p + 1; q < n; q++) {
+        const double apq = A[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        A[p][p] -= t * apq; A[q][q] += t * apq; A[p][q] = 0.0;
+        PNP_ROLLED
+        for (int k = 0; k < n; k++) {
+          if (k != p && k != q) {
+            // element (k, p) and (k, q) of the symmetric matrix, read from / written to the upper triangle
+            double* ep = k < p ? &A[k][p] : &A[p][k];
+            double* eq = k < q ? &A[k][q] : &A[q][k];
+            const double akp = *ep, akq = *eq;
+            *ep = c * akp - s * akq; *eq = s * akp + c * akq;
+          }
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq;
+        }
+      }
+    }
+  }
+  return sweep;
+}
+
+template <int n>
+SSP_HD int jacobi_eig_twosided(double A[n][n], double V[n][n]) {
   for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i][j] = (i == j) ? 1.0 : 0.0;
   int sweep = 0;
   for (; sweep < 30; sweep++) {
     double off = 0.0, diag = 0.0;
     for (int i = 0; i < n; i++) { diag += A[i][i] * A[i][i]; for (int j = i + 1; j < n; j++) off += A[i][j] * A[i][j]; }
     if (off <= 1e-34 * diag || off == 0.0) break;
+#if PNP_JACOBI_VARIANT == 1      // probe: the same arithmetic with the pivot loops kept rolled
+    PNP_ROLLED
+#endif
     for (int p = 0; p < n - 1; p++)
+#if PNP_JACOBI_VARIANT == 1
+      PNP_ROLLED
+#endif
       for (int q = p + 1; q < n; q++) {
         if (A[p][q] == 0.0) continue;
         const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
@@ -70,6 +136,15 @@ SSP_HD int jacobi_eig(double A[n][n], double V[n][n]) {
       }
   }
   return sweep;
+}
+
+template <int n>
+SSP_HD int jacobi_eig(double A[n][n], double V[n][n]) {
+#if PNP_JACOBI_VARIANT == 0 || PNP_JACOBI_VARIANT == 1
+  return jacobi_eig_twosided<n>(A, V);
+#else
+  return jacobi_eig_upper<n>(A, V);
+#endif
 }
 
 // in-place Cholesky solve of SPD n x n system (n <= 6); returns false if not positive definite

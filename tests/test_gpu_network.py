@@ -248,7 +248,7 @@ def test_fused_sgd_repack_and_bucketed_step_match_plain(cfg_path, monkeypatch):
     x, tgt = synth.images(2, seed=13).cuda(), synth.targets(2, seed=14)
     crit = RegionLoss(); crit.verbose = False
     outs = []
-    for mode in ("plain", "fused", "bucketed"):
+    for mode in ("plain", "plain", "fused", "bucketed"):      # the second plain run measures the run-to-run noise of step 2
         m = copy.deepcopy(base)
         opt = FlatSGD(m, lr=1e-4, momentum=0.9, weight_decay=0.032)
         opt.fused = mode != "plain"
@@ -267,13 +267,18 @@ def test_fused_sgd_repack_and_bucketed_step_match_plain(cfg_path, monkeypatch):
             if it == 0:
                 first = [p.detach().clone() for p in m.parameters()]
         outs.append((logits, first, [p.detach().clone() for p in m.parameters()]))
-    for logits, first, params in outs[1:]:
+    # Step 2 re-amplifies the 1e-7 weight differences that the fp32 atomics' summation order leaves after step 1 (chaotic net):
+    # parameters that start at zero (BN beta, the head's bias) are pure sums of gradients after two steps, so their relative
+    # difference IS the gradient noise.  The floor is measured here -- plain vs plain -- instead of guessed (B200, round 2: a
+    # fixed 2e-3 failed at 4.4e-3 on a bias of magnitude 3e-5).
+    floor = [_rel(p, q) for p, q in zip(outs[1][2], outs[0][2])]
+    for logits, first, params in outs[2:]:
         assert torch.equal(logits[0], outs[0][0][0])
         for p, q in zip(first, outs[0][1]):
             assert _rel(p, q) < 1e-6                          # one step: the same update up to the atomics' summation order
         assert _rel(logits[1], outs[0][0][1]) < 1e-4          # second forward used the planes the optimiser wrote
-        for p, q in zip(params, outs[0][2]):
-            assert _rel(p, q) < 2e-3                          # second step: 1e-7 weight differences re-amplified by the chaotic net
+        for p, q, fl in zip(params, outs[0][2], floor):
+            assert _rel(p, q) < max(2e-3, 4.0 * fl) and _rel(p, q) < 5e-2
 
 
 def _grad_errors(model_params, ref_params):
