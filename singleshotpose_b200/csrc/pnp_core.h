@@ -51,11 +51,12 @@ SSP_HD void rodrigues(const double r[3], double R[9], double* J /*27 or null: dR
 
 // cyclic Jacobi on a symmetric n x n matrix: A -> diag, V = eigenvectors (columns); returns the number of sweeps.
 // Works on the upper triangle only, each rotation through scalar temporaries (the textbook form: the pivot is set to zero and
-// the diagonal updated by t*a_pq exactly, symmetry cannot drift), loops kept rolled.  Round 2, B200: the two-sided form that
-// rotated whole columns and then whole rows in place (jacobi_eig_twosided below, kept for the probe) is right on the host and at
-// nvcc -O0 but does NOT converge as device code at -O3 for n = 12 (tools/probes/pnp_probe.cu: 128 of 128 problems wrong,
-// negative "eigenvalues" of a PSD matrix; -fmad=false makes no difference) -- nvcc unrolls the outer pivot loop and re-orders the
-// overlapping column / row updates.
+// the diagonal updated by t*a_pq exactly, symmetry cannot drift), loops kept rolled.  Round 2, B200 (tools/probes/pnp_probe.cu,
+// profiles/r02_pnp_probe.txt): the two-sided form that rotates whole columns and then whole rows in place (jacobi_eig_twosided
+// below, kept for the probe) is right on the host and as device code at -O0, but as -O3 device code for n = 12 it does not
+// converge (128 of 128 problems wrong, negative "eigenvalues" of a PSD matrix, with and without -fmad=false).  The same arithmetic
+// with `#pragma unroll 1` on the two pivot loops (variant 1) is right again: nvcc 12.9's unrolling of the pivot loop over the
+// overlapping column / row updates is what breaks it.  Variant 2 (this function) is the default.
 #ifndef PNP_JACOBI_VARIANT
 #define PNP_JACOBI_VARIANT 2
 #endif
