@@ -34,6 +34,7 @@ extern "C" {
 #define SSP_IMPL_SIMT 1  /* fp32 CUDA-core kernel (cross-check / bring-up) */
 #define SSP_IMPL_BAND 3  /* narrow 3x3 layers: one activation band per kernel row + resident weights (falls back to TC) */
 #define SSP_IMPL_TC2 2   /* tcgen05 cta_group::2 kernel: CTA pairs share the weight tile (ssp_conv_gemm only) */
+#define SSP_IMPL_BANDT 4 /* few output channels (<= 64 split-fp16, <= 128 single-term): operands swapped, weights on the M side, 128/256 pixels as N (csrc/conv_bandt.cu; falls back to BAND / TC2 / TC when not eligible) */
 #define SSP_EPI_F32 0    /* store fp32 */
 #define SSP_EPI_STATS 1  /* store fp32 + per-channel sum / sum of squares over valid pixels (fp64) */
 #define SSP_EPI_BIAS 2   /* add bias, store fp32 */
@@ -61,6 +62,8 @@ int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo_or_null, long lon
                   const void* b_hi, const void* b_lo_or_null, int b_rows, int b_ld, int a_fmt, int b_fmt,
                   int N, int H, int W, int taps, int cout, float* out, int out_ld, long long out_rows, int epi,
                   const float* bias, double* stat_sum, double* stat_sq, void* stream);
+/* number of launches of the operand-swapped kernel (SSP_IMPL_BANDT) so far in this process: lets a test tell the kernel from its fall-backs */
+int ssp_conv_bandt_launches(void);
 /* ---- inference: nn.Conv2d + nn.BatchNorm2d(eval) + nn.LeakyReLU as ONE kernel (darknet.py:154-164 under model.eval()):
  *      z = leaky(conv * scale[c] + shift[c]) is written by the GEMM epilogue straight into the consumer's fp16 hi/lo operand
  *      planes (rows [row][d_ld], channel offset d_c0); scale/shift from ssp_bn_finalize(train=0).  fp16 hi/lo operands. ---- */
@@ -72,6 +75,20 @@ int ssp_conv_gemm_bnact(int impl, const void* a_hi, const void* a_lo, long long 
  *      fp32 master weights [32][3][3][3] (k = (kh*3+kw)*3 + ci), output rows [row(n,h,w)][y_ld], optional fp64 BN statistics ---- */
 int ssp_conv0_direct(const float* x_nchw, const float* w, const float* bias_or_null, float* y, int y_ld,
                      double* stat_sum_or_null, double* stat_sq_or_null, int N, int H, int W, void* stream);
+/* ---- blocks 0-1 of cfg/yolo-pose.cfg as a unit -- nn.Conv2d(3,32,3,1,1) + BatchNorm2d + LeakyReLU + MaxPool2d(2,2) (darknet.py:154-167)
+ *      and their autograd (train.py:103) -- without materialising the full-resolution conv output (csrc/l0_fused.cu).
+ *      gram: double[28*28] (upper triangle: sums of q q^T over all pixels, q = (27 patch values, 1)), kept from forward to backward;
+ *      code: uint8 [pooled rows][32] (bits 0-1 arg-max position of the 2x2 window, bit 2 pre-activation > 0);
+ *      t1: double[28*32] scratch (27 x 32 patch-weighted gradient sums + the 32 plain sums).  w = fp32 master weights [32][27].
+ *      ssp_l0_stats writes the per-channel sum / sum of squares that ssp_bn_finalize(count = N*H*W) expects. ---- */
+int ssp_l0_gram(const float* x_nchw, int N, int H, int W, double* gram, void* stream);
+int ssp_l0_stats(const double* gram, const float* w, double* stat_sum, double* stat_sq, void* stream);
+int ssp_l0_fused_fwd(const float* x_nchw, const float* w, const float* scale, const float* shift, float slope, int N, int H, int W,
+                     void* d_hi, void* d_lo, int d_ld, int d_c0, unsigned char* code_or_null, void* stream);
+int ssp_l0_bwd(const float* x_nchw, const float* g_pooled, int g_ld, int g_c0, const unsigned char* code, float slope, int N, int H,
+               int W, double* t1, void* stream);
+int ssp_l0_bwd_finalize(const double* t1, const double* gram, const float* w, const float* gamma, const float* mean,
+                        const float* invstd, double count, float grad_scale, float* dw, float* dgamma, float* dbeta, void* stream);
 /* ---- nn.Conv2d weight gradient: dW[co][tap][ci] += scale * sum_m dY[m][co] * X[m + shift(tap)][ci] ---- */
 int ssp_wgrad_gemm(int impl, const void* dy, long long dy_rows, int dy_ld, int cout, int dy_fmt, const void* x,
                    long long x_rows, int x_ld, int cin, int x_fmt, int N, int H, int W, int taps, float* dw,

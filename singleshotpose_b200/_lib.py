@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SSP_LIB") or os.path.join(_HERE, "csrc", "libssp_b200.so")   # SSP_LIB: A/B experiments only
 
 FMT_F16, FMT_BF16 = 0, 1
-IMPL_TC, IMPL_SIMT, IMPL_TC2, IMPL_BAND = 0, 1, 2, 3
+IMPL_TC, IMPL_SIMT, IMPL_TC2, IMPL_BAND, IMPL_BANDT = 0, 1, 2, 3, 4
 EPI_F32, EPI_STATS, EPI_BIAS = 0, 1, 2
 ROUTE_NONE, ROUTE_DIRECT, ROUTE_POOL, ROUTE_REORG = 0, 1, 2, 3
 
@@ -26,7 +26,13 @@ SIGNATURES = {
     "ssp_unpack_nchw": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "ssp_unpack16_nchw": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "ssp_conv_gemm": [_i, _p, _p, _ll, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _ll, _i, _p, _p, _p, _p],
+    "ssp_conv_bandt_launches": [],
     "ssp_conv0_direct": [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _p],
+    "ssp_l0_gram": [_p, _i, _i, _i, _p, _p],
+    "ssp_l0_stats": [_p, _p, _p, _p, _p],
+    "ssp_l0_fused_fwd": [_p, _p, _p, _p, _f, _i, _i, _i, _p, _p, _i, _i, _p, _p],
+    "ssp_l0_bwd": [_p, _p, _i, _i, _p, _f, _i, _i, _i, _p, _p],
+    "ssp_l0_bwd_finalize": [_p, _p, _p, _p, _p, _p, _d, _f, _p, _p, _p, _p],
     "ssp_conv_gemm_bnact": [_i, _p, _p, _ll, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _i, _i, _p],
     "ssp_wgrad_gemm": [_i, _p, _ll, _i, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _f, _p],
     "ssp_bn_finalize": [_p, _p, _d, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _i, _p],

@@ -21,7 +21,15 @@ int conv_gemm_band(const void*, const void*, long long, int, int, const void*, c
                    float*, int, long long, int, const float*, double*, double*, cudaStream_t);
 int conv_gemm_simt(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
                    float*, int, long long, int, const float*, double*, double*, cudaStream_t);
+int conv_gemm_bandt(const void*, const void*, long long, int, int, const void*, const void*, int, int, int, int, int, int, int, int, int,
+                    float*, int, long long, int, const float*, double*, double*, cudaStream_t);
+int conv_bandt_launch_count();
 int conv0_direct(const float*, const float*, const float*, float*, int, double*, double*, int, int, int, cudaStream_t);
+int l0_gram(const float*, int, int, int, double*, cudaStream_t);
+int l0_stats(const double*, const float*, double*, double*, cudaStream_t);
+int l0_fused_fwd(const float*, const float*, const float*, const float*, float, int, int, int, void*, void*, int, int, uint8_t*, cudaStream_t);
+int l0_bwd(const float*, const float*, int, int, const uint8_t*, float, int, int, int, double*, cudaStream_t);
+int l0_bwd_finalize(const double*, const double*, const float*, const float*, const float*, const float*, double, float, float*, float*, float*, cudaStream_t);
 int wgrad_gemm_tc(const void*, long long, int, int, int, const void*, long long, int, int, int, int, int, int, int, float*, int, int, float, cudaStream_t);
 int wgrad_gemm_simt(const void*, long long, int, int, int, const void*, long long, int, int, int, int, int, int, int, float*, int, int, float, cudaStream_t);
 int wgrad_gemm_tc2(const void*, long long, int, int, int, const void*, long long, int, int, int, int, int, int, int, float*, int, int, float, cudaStream_t);
@@ -81,6 +89,11 @@ int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo, long long a_rows
                   long long out_rows, int epi, const float* bias, double* ssum, double* ssq, void* s) {
   if (impl == SSP_IMPL_SIMT)
     return conv_gemm_simt(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
+  if (impl == SSP_IMPL_BANDT) {
+    const int rc = conv_gemm_bandt(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
+    if (rc != 1) return rc;          // 1 = not eligible: the kernels for wider layers below
+    impl = (taps == 9 && cout < 128) ? SSP_IMPL_BAND : (cout >= 128 ? SSP_IMPL_TC2 : SSP_IMPL_TC);
+  }
   if (impl == SSP_IMPL_BAND) {
     const int rc = conv_gemm_band(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
     if (rc != 1) return rc;          // 1 = layer not eligible (weights do not fit): per-tap kernel below
@@ -89,8 +102,22 @@ int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo, long long a_rows
     return conv_gemm_tc2(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s), nullptr);
   return conv_gemm_tc(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s), nullptr);
 }
+int ssp_conv_bandt_launches(void) { return conv_bandt_launch_count(); }
 int ssp_conv0_direct(const float* x, const float* w, const float* bias, float* y, int y_ld, double* ssum, double* ssq, int N, int H, int W, void* s) {
   return conv0_direct(x, w, bias, y, y_ld, ssum, ssq, N, H, W, ST(s));
+}
+int ssp_l0_gram(const float* x, int N, int H, int W, double* gram, void* s) { return l0_gram(x, N, H, W, gram, ST(s)); }
+int ssp_l0_stats(const double* gram, const float* w, double* ssum, double* ssq, void* s) { return l0_stats(gram, w, ssum, ssq, ST(s)); }
+int ssp_l0_fused_fwd(const float* x, const float* w, const float* scale, const float* shift, float slope, int N, int H, int W, void* d_hi,
+                     void* d_lo, int d_ld, int d_c0, unsigned char* code, void* s) {
+  return l0_fused_fwd(x, w, scale, shift, slope, N, H, W, d_hi, d_lo, d_ld, d_c0, code, ST(s));
+}
+int ssp_l0_bwd(const float* x, const float* g, int g_ld, int g_c0, const unsigned char* code, float slope, int N, int H, int W, double* t1, void* s) {
+  return l0_bwd(x, g, g_ld, g_c0, code, slope, N, H, W, t1, ST(s));
+}
+int ssp_l0_bwd_finalize(const double* t1, const double* gram, const float* w, const float* gamma, const float* mean, const float* invstd,
+                        double count, float gscale, float* dw, float* dgamma, float* dbeta, void* s) {
+  return l0_bwd_finalize(t1, gram, w, gamma, mean, invstd, count, gscale, dw, dgamma, dbeta, ST(s));
 }
 int ssp_conv_gemm_bnact(int impl, const void* a_hi, const void* a_lo, long long a_rows, int a_ld, int cin, const void* b_hi, const void* b_lo,
                         int b_rows, int b_ld, int N, int H, int W, int taps, int cout, const float* scale, const float* shift, float slope,

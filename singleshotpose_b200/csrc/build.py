@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["abi.cu", "conv_tc.cu", "conv_tc2.cu", "conv_band.cu", "wgrad_tc.cu", "wgrad_tc2.cu", "conv_simt.cu", "conv0_direct.cu", "elementwise.cu", "sgd_pack.cu", "region.cu", "region_multi.cu", "pnp.cu", "augment.cu"]
+SOURCES = ["abi.cu", "conv_tc.cu", "conv_tc2.cu", "conv_band.cu", "conv_bandt.cu", "wgrad_tc.cu", "wgrad_tc2.cu", "conv_simt.cu", "conv0_direct.cu", "l0_fused.cu", "elementwise.cu", "sgd_pack.cu", "region.cu", "region_multi.cu", "pnp.cu", "augment.cu"]
 # augment.cu restates Pillow's float/double pixel arithmetic bit for bit: no multiply-add contraction there
 EXTRA = {"augment.cu": ["-fmad=false"]}
 for _env, _macro in (("SSP_BN_MINBLOCKS", "SSP_BN_MINBLOCKS"), ("SSP_BN_UNITS", "BN_UNITS_PER_THREAD"),

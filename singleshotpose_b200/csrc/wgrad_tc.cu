@@ -9,9 +9,15 @@
 // 512/BN taps) -- the kernel is L2->SMEM bandwidth bound, sharing dY across taps is what matters.  Partial sums
 // are reduced with fp32 RED atomics into dW, which the caller zeroes once per step.  Output layout [co][tap][ci] is the layout the
 // master weights are kept in (engine.py), i.e. the gradient of nn.Conv2d.weight seen through a permuted view.
+// Round 2: the X boxes of consecutive taps sit at a constant distance in shared memory and their accumulators in adjacent TMEM
+// columns, which is exactly the MN-major operand's "next 64-element N group at LBO" rule -- so up to 256 / 64 taps go into ONE
+// tcgen05.mma of N = 256 instead of one N = 64 instruction per tap (an MMA with N <= 64 costs ~95 clk whatever its size: the narrow
+// layers were issue-bound, block 2's weight gradient ran 545 us at batch 64).  Narrow layers therefore use a 64-column accumulator
+// stride per tap (cin <= 32 leaves the upper half of each group zero).
 // Replaces the conv weight-gradient autograd computes for reference train.py:103.
 #include "ssp_common.cuh"
 #include "tmap.cuh"
+#include <stdlib.h>
 
 namespace ssp {
 
@@ -24,7 +30,9 @@ struct WgradTcParams {
   int kblocks_total;    // ceil(m_rows / 64)
   int shifts[9];
   int cout, cin, bn;
-  uint32_t idesc;
+  int acc_stride;       // TMEM columns per tap accumulator (>= bn; 64 for bn = 32 so that taps merge into one N-wide MMA)
+  int merge;            // taps per MMA (1 = one instruction per tap)
+  uint32_t idesc;       // N field left zero: filled per instruction
   int stages, stage_bytes;
   float* dw;
   int dw_ld, cin_store;  // row pitch of dW per (co, tap) and number of real input channels
@@ -100,18 +108,20 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
         const int buf = n % p.nbuf, use = n / p.nbuf;
         mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.taps_per_group * p.bn);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.taps_per_group * p.acc_stride);
         uint32_t acc = 0;
         for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t s = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          for (int t = 0; t < ntap; t++) {
+          for (int t = 0; t < ntap; t += p.merge) {
+            const int g = ntap - t < p.merge ? ntap - t : p.merge;                       // taps in this instruction
+            const uint32_t idesc = p.idesc | ((uint32_t)((p.merge > 1 ? g * p.acc_stride : p.bn) >> 3) << 17);
 #pragma unroll
             for (int k = 0; k < 4; k++) {   // 16 K rows per MMA = 2 swizzle groups of 8 rows = 2048 B
               const uint64_t da = umma_desc_sw128(s + k * 2048, kBox, 1024);
               const uint64_t db = umma_desc_sw128(s + (2 + t * nb) * kBox + k * 2048, kBox, 1024);
-              umma_f16(d_tmem + (uint32_t)(t * p.bn), da, db, p.idesc, (k == 0) ? acc : 1u);
+              umma_f16(d_tmem + (uint32_t)(t * p.acc_stride), da, db, idesc, (k == 0) ? acc : 1u);
             }
           }
           acc = 1;
@@ -131,7 +141,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
       tc_fence_after();
       const int co = co_t * 128 + q * 32 + lane;
       for (int t = 0; t < ntap; t++) {
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.taps_per_group + t) * p.bn);
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.taps_per_group + t) * p.acc_stride);
         float* drow = p.dw + ((long long)co * p.taps + tap0 + t) * p.dw_ld;
         for (int ch = 0; ch < p.bn / 32; ch++) {
           uint32_t r[32];
@@ -176,10 +186,13 @@ int wgrad_gemm_tc(const void* dy, long long dy_rows, int dy_ld, int cout, int dy
   const int nb = bn <= 64 ? 1 : bn / 64;
   // sharing dY across taps pays for narrow tiles (L2-bound, deep pipeline still fits); for BN >= 128 the shallower
   // smem ring and the single TMEM buffer cost more than the saved traffic (measured), so one tap per item there
-  int tmax = (bn <= 64) ? 512 / bn : 1; if (tmax > taps) tmax = taps;
+  static const int merge_on = []() { const char* e = getenv("SSP_WGRAD_MERGE"); return e ? atoi(e) : 1; }();
+  p.acc_stride = (merge_on && bn < 64) ? 64 : bn;
+  p.merge = (merge_on && taps > 1 && p.acc_stride <= 128) ? 256 / p.acc_stride : 1;
+  int tmax = (bn <= 64) ? 512 / p.acc_stride : (p.merge > 1 ? p.merge : 1); if (tmax > taps) tmax = taps;
   p.groups = (taps + tmax - 1) / tmax;
   p.taps_per_group = (taps + p.groups - 1) / p.groups;
-  p.nbuf = (2 * p.taps_per_group * bn <= 512) ? 2 : 1;
+  p.nbuf = (2 * p.taps_per_group * p.acc_stride <= 512) ? 2 : 1;
   p.m_rows = g.m_rows();
   p.kblocks_total = (int)((p.m_rows + 63) / 64);
   p.co_tiles = (cout + 127) / 128;
@@ -194,7 +207,7 @@ int wgrad_gemm_tc(const void* dy, long long dy_rows, int dy_ld, int cout, int dy
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.splits = splits;
-  p.idesc = umma_idesc_f16(dy_fmt, x_fmt, 1, 1, bn);
+  p.idesc = umma_idesc_f16(dy_fmt, x_fmt, 1, 1, 0);
   p.stage_bytes = (2 + p.taps_per_group * nb) * kBox;
   const int fixed = (2 * kMaxStagesW + 4) * 8 + 16 + 1024;
   int stages = (227 * 1024 - fixed) / p.stage_bytes;

@@ -143,6 +143,16 @@ class Buffers:
             rows = _lib.flat_alloc_rows(N, h, w)
             cin_total = L.k_cin if L.first else L.cin
             self.rows.append(rows)
+            if L.first and eng.l0_fused:
+                # blocks 0-1 run as one unit (csrc/l0_fused.cu): no im2col plane, no full-resolution conv output, no dY plane --
+                # the 28x28 Gram matrix of the image patches, a 1-byte code per pooled cell and 28x32 backward sums instead
+                self.x_hi.append(None); self.x_lo.append(None); self.y.append(None)
+                self.l0_gram = torch.zeros(28 * 28, dtype=torch.float64, device=dev)
+                if train:
+                    self.l0_code = torch.zeros(_lib.flat_alloc_rows(N, h // 2, w // 2), 32, dtype=torch.uint8, device=dev)
+                    self.l0_t1 = torch.zeros(28 * 32, dtype=torch.float64, device=dev)
+                    self.ypool.append(None); self.dy.append(None); self.dx.append(None)
+                continue
             self.x_hi.append(torch.zeros(rows, cin_total, dtype=f16, device=dev))
             self.x_lo.append(torch.zeros(rows, cin_total, dtype=f16, device=dev))
             self.y.append(torch.zeros(rows, _rup(L.cout, 4), dtype=torch.float32, device=dev))
@@ -170,6 +180,7 @@ class Engine:
         self.conv_impl = {"simt": _lib.IMPL_SIMT, "tc2": _lib.IMPL_TC2, "tc": _lib.IMPL_TC, "auto": -1}.get(impl, -1)
         self.tc2_min_n = int(os.environ.get("SSP_TC2_MIN_N", "128"))
         self.use_band = os.environ.get("SSP_BAND", "1") != "0"
+        self.use_bandt = os.environ.get("SSP_BANDT", "1") != "0"
         self.fuse_eval = os.environ.get("SSP_FUSE_EVAL", "1") != "0"
         self.pack_fn = "ssp_pack_weights"
         wimpl = os.environ.get("SSP_WGRAD_IMPL", "simt" if impl == "simt" else "tc2").lower()
@@ -191,6 +202,13 @@ class Engine:
         self.profile = None          # set to [] to record (kind, layer block, algorithmic flops, start event, end event) per GEMM launch
         net = model.blocks[0]
         self.base_hw = (int(net["height"]), int(net["width"]))
+        # SSP_L0: "fused" (default) = conv + BN + leaky + 2x2 max-pool of blocks 0-1 as one unit from the raw image, statistics from
+        # the patch Gram matrix, backward over the pooled gradient (csrc/l0_fused.cu); "direct" = fp32 direct conv writing the
+        # full-resolution Y (round-1/2 path); "gemm" = im2col + tensor-core GEMM (bring-up path).
+        self.l0_mode = os.environ.get("SSP_L0", "fused").lower()
+        f = self.layers[0]
+        self.l0_fused = (self.l0_mode == "fused" and self.conv_impl != _lib.IMPL_SIMT and not self.fast and f.bn and f.cout == 32
+                         and len(f.dests) == 1 and f.dests[0][2] == _lib.ROUTE_POOL)
 
     # ------------------------------------------------------------------ geometry
     def spatial(self, L, H, W):
@@ -359,9 +377,13 @@ class Engine:
             self._buffers[key] = b
         return b
 
-    def _conv_impl(self, n_out, taps=1):
+    def _conv_impl(self, n_out, taps=1, terms=3):
         if self.conv_impl >= 0:
             return self.conv_impl
+        # few output channels: operands swapped (weights on the M side, 128 / 256 pixels as the MMA's N; csrc/conv_bandt.cu).
+        # The ABI falls back to the kernels below by itself when the layer's weights do not fit next to two activation bands.
+        if self.use_bandt and n_out <= (64 if terms == 3 else 128):
+            return _lib.IMPL_BANDT
         if n_out >= self.tc2_min_n:
             return _lib.IMPL_TC2
         return _lib.IMPL_BAND if (taps == 9 and self.use_band) else _lib.IMPL_TC
@@ -380,7 +402,7 @@ class Engine:
 
     def _conv_fwd(self, L, B, N, h, w, xin, a_lo, b_lo, epi, bias, st, s):
         i = L.index
-        self._gemm("fwd", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cout, L.k_taps), ptr(xin), a_lo, B.rows[i], xin.shape[1], L.k_cin,
+        self._gemm("fwd", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cout, L.k_taps, 1 if self.fast else 3), ptr(xin), a_lo, B.rows[i], xin.shape[1], L.k_cin,
                    ptr(self.w_hi[i]), b_lo, L.cout, self.w_hi[i].shape[1], _lib.FMT_F16, _lib.FMT_F16,
                    N, h, w, L.k_taps, L.cout, ptr(B.y[i]), B.y[i].shape[1], B.rows[i], epi, bias,
                    ptr(st["ssum"]), ptr(st["ssq"]), s)
@@ -398,8 +420,11 @@ class Engine:
         B.generation += 1
         s = stream_ptr()
         mods = self.conv_modules()
-        direct0 = self.conv_impl != _lib.IMPL_SIMT and not self.fast and os.environ.get("SSP_L0", "direct") == "direct"
-        if not direct0 or keep_for_backward:       # the im2col'ed plane feeds the tensor-core GEMMs (forward unless direct, wgrad always)
+        direct0 = self.conv_impl != _lib.IMPL_SIMT and not self.fast and self.l0_mode in ("direct", "fused")
+        B.x_image = x if self.l0_fused else None   # the layer-0 backward reads the image again (kept alive with the activations)
+        if self.l0_fused:
+            pass
+        elif not direct0 or keep_for_backward:     # the im2col'ed plane feeds the tensor-core GEMMs (forward unless direct, wgrad always)
             call("ssp_pack_input_im2col", ptr(x), ptr(B.x_hi[0]), None if direct0 else ptr(B.x_lo[0]), N, H, W, s)
             self.launches += 1
         for L in self.layers:
@@ -423,10 +448,26 @@ class Engine:
                 call("ssp_bn_finalize", None, None, 1.0, ptr(bn.weight.data), ptr(bn.bias.data), ptr(bn.running_mean), ptr(bn.running_var),
                      0.1, float(bn.eps), 0, ptr(st["mean"]), ptr(st["invstd"]), ptr(st["scale"]), ptr(st["shift"]), L.cout, s)
                 ci, c0, _k = L.dests[0]
-                self._gemm("fwd", L, N, h, w, "ssp_conv_gemm_bnact", self._conv_impl(L.cout, L.k_taps), ptr(xin), a_lo, B.rows[i], xin.shape[1],
+                self._gemm("fwd", L, N, h, w, "ssp_conv_gemm_bnact", self.conv_impl if self.conv_impl >= 0 else (_lib.IMPL_TC2 if L.cout >= self.tc2_min_n else _lib.IMPL_TC), ptr(xin), a_lo, B.rows[i], xin.shape[1],
                            L.k_cin, ptr(self.w_hi[i]), b_lo, L.cout, self.w_hi[i].shape[1], N, h, w, L.k_taps, L.cout,
                            ptr(st["scale"]), ptr(st["shift"]), L.slope, ptr(B.x_hi[ci]), ptr(B.x_lo[ci]), B.x_hi[ci].shape[1], c0, s)
                 self.launches += 1          # bn_finalize (the GEMM is counted by _gemm)
+                continue
+            if L.first and self.l0_fused:
+                off, n, _gv = self._slices[id(conv.weight)]
+                w0 = ptr(self.flat_params[off:off + n])
+                if train_bn:       # batch statistics of the conv output from the Gram matrix of the image patches (no pass over y)
+                    call("ssp_l0_gram", ptr(x), N, H, W, ptr(B.l0_gram), s)
+                    call("ssp_l0_stats", ptr(B.l0_gram), w0, ptr(st["ssum"]), ptr(st["ssq"]), s)
+                    self.launches += 2
+                call("ssp_bn_finalize", ptr(st["ssum"]) if train_bn else None, ptr(st["ssq"]) if train_bn else None, float(N * h * w),
+                     ptr(bn.weight.data), ptr(bn.bias.data), ptr(bn.running_mean), ptr(bn.running_var),
+                     float(bn.momentum if bn.momentum is not None else 0.1), float(bn.eps), 1 if train_bn else 0,
+                     ptr(st["mean"]), ptr(st["invstd"]), ptr(st["scale"]), ptr(st["shift"]), L.cout, s)
+                ci, c0, _k = L.dests[0]
+                call("ssp_l0_fused_fwd", ptr(x), w0, ptr(st["scale"]), ptr(st["shift"]), L.slope, N, H, W, ptr(B.x_hi[ci]), ptr(B.x_lo[ci]),
+                     B.x_hi[ci].shape[1], c0, ptr(B.l0_code) if keep_for_backward else None, s)
+                self.launches += 2
                 continue
             if L.first and direct0 and L.bn:       # exact fp32 direct convolution of the raw image (HBM-bound layer)
                 off, n, _gv = self._slices[id(conv.weight)]
@@ -485,6 +526,24 @@ class Engine:
             h, w = self.spatial(L, H, W)
             st = B.stat[i]
             dy = B.dy[i]
+            if L.first and self.l0_fused:
+                # dW0 / dgamma / dbeta from the pooled gradient, the arg-max codes and the image (csrc/l0_fused.cu); runs where the
+                # weight gradients run, after the data gradient of layer 1 (the last kernel of the main stream)
+                ci, c0, _k = L.dests[0]
+                off, n, _gv = self._slices[id(conv.weight)]
+                if overlap:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                self._gemm("wgrad", L, N, h, w, "ssp_l0_bwd", ptr(B.x_image), ptr(B.dx[ci]), B.dx[ci].shape[1], c0, ptr(B.l0_code), L.slope,
+                           N, H, W, ptr(B.l0_t1), ws, stream=wstream)
+                call("ssp_l0_bwd_finalize", ptr(B.l0_t1), ptr(B.l0_gram), ptr(self.flat_params[off:off + n]), ptr(bn.weight.data),
+                     ptr(st["mean"]), ptr(st["invstd"]), float(N * h * w), inv, ptr(self.flat_grads[off:off + n]),
+                     ptr(self.grad_view(bn.weight)), ptr(self.grad_view(bn.bias)), ws)
+                self.launches += 1
+                if self.grad_ready_hook is not None:
+                    self.grad_ready_hook(i, side if overlap else main)
+                continue
             if L.bn:
                 srcs = []
                 for (ci, c0, kind) in L.dests:
@@ -526,7 +585,7 @@ class Engine:
                 ev.record(main)                      # dY of this layer is complete
             if not L.first:                          # data gradient first: it is on the critical path of the next layer
                 wd = self.w_d[i]
-                self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cin, L.taps), ptr(dy), None, B.rows[i], dy.shape[1], L.cout,
+                self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cin, L.taps, 1), ptr(dy), None, B.rows[i], dy.shape[1], L.cout,
                            ptr(wd), None, L.cin, wd.shape[1], self.grad_fmt, self.grad_fmt, N, h, w, L.taps, L.cin, ptr(B.dx[i]),
                            B.dx[i].shape[1], B.rows[i], _lib.EPI_F32, None, None, None, s)
             if overlap:

@@ -78,7 +78,7 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("impl", [_lib.IMPL_SIMT, _lib.IMPL_TC, _lib.IMPL_TC2, _lib.IMPL_BAND])
+@pytest.mark.parametrize("impl", [_lib.IMPL_SIMT, _lib.IMPL_TC, _lib.IMPL_TC2, _lib.IMPL_BAND, _lib.IMPL_BANDT])
 def test_conv_gemm_matches_torch(case, impl):
     N, H, W, cin, cout, k, use_bias = case
     g = torch.Generator().manual_seed(hash(case) % 1000)
@@ -116,7 +116,7 @@ def test_conv_gemm_single_term_bf16_dgrad_layout():
     w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
     dyq = dy.bfloat16().float(); wq = w.bfloat16().float()
     ref = F.conv_transpose2d(dyq.double(), wq.double(), padding=1).float()
-    for impl in (_lib.IMPL_SIMT, _lib.IMPL_TC, _lib.IMPL_TC2, _lib.IMPL_BAND):
+    for impl in (_lib.IMPL_SIMT, _lib.IMPL_TC, _lib.IMPL_TC2, _lib.IMPL_BAND, _lib.IMPL_BANDT):
         dyh, _, rows = flat_from_nchw(dy.to(DEV), fmt=_lib.FMT_BF16, split=False)
         _, _, wd = _pack_w(w.to(DEV), fmt=_lib.FMT_BF16, dgrad=True)
         dx = torch.zeros(rows, cin, device=DEV)
@@ -127,7 +127,10 @@ def test_conv_gemm_single_term_bf16_dgrad_layout():
         assert (out - ref).abs().max() / ref.abs().max() < 1e-4, impl
 
 
-WGRAD_CASES = [(2, 12, 12, 64, 64, 3), (1, 13, 13, 256, 128, 3), (2, 26, 26, 128, 64, 1), (2, 13, 13, 1024, 20, 1), (3, 5, 7, 64, 256, 3)]
+WGRAD_CASES = [(2, 12, 12, 64, 64, 3), (1, 13, 13, 256, 128, 3), (2, 26, 26, 128, 64, 1), (2, 13, 13, 1024, 20, 1), (3, 5, 7, 64, 256, 3),
+               (2, 20, 12, 32, 64, 3),      # cin 32: four taps per N = 256 instruction, 64-column accumulator stride (block 2)
+               (2, 13, 13, 128, 256, 3),    # cin 128: two taps per instruction, five tap groups
+               (1, 30, 22, 64, 128, 3)]     # cin 64 (blocks 3 / 5)
 
 
 @pytest.mark.parametrize("case", WGRAD_CASES)
@@ -405,3 +408,156 @@ def test_conv0_direct_matches_torch(shape):
     idx = torch_flat_index(N, H, W)
     mask = torch.ones(rows, dtype=torch.bool); mask[idx] = False
     assert float(y.cpu()[mask].abs().max()) == 0.0                       # pad rows untouched
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 64), (1, 48, 80), (3, 16, 32), (2, 34, 70)])
+def test_l0_fused_blocks_match_torch(shape):
+    """blocks 0-1 as one unit (csrc/l0_fused.cu: conv 3->32 + BatchNorm(batch statistics) + LeakyReLU + MaxPool 2x2, darknet.py:154-167)
+    and their backward, against torch fp64 autograd of the same modules: Gram-matrix statistics, the pooled operand planes + arg-max
+    codes, dW / dgamma / dbeta from the pooled gradient.  Shapes cover partial tiles in both directions."""
+    N, H, W = shape
+    g = torch.Generator().manual_seed(23)
+    x = torch.rand(N, 3, H, W, generator=g)
+    w = (torch.randn(32, 3, 3, 3, generator=g) * 0.3)
+    gamma = torch.rand(32, generator=g) + 0.5
+    beta = torch.randn(32, generator=g) * 0.2
+    gpool = torch.randn(N, 32, H // 2, W // 2, generator=g)
+    # ---- reference: fp64 autograd
+    wd = w.double().requires_grad_(True); gd = gamma.double().requires_grad_(True); bd = beta.double().requires_grad_(True)
+    y = F.conv2d(x.double(), wd, padding=1)
+    mean = y.mean(dim=(0, 2, 3)); var = y.var(dim=(0, 2, 3), unbiased=False)
+    eps = 1e-4
+    z = (y - mean[None, :, None, None]) / torch.sqrt(var + eps)[None, :, None, None] * gd[None, :, None, None] + bd[None, :, None, None]
+    a = F.leaky_relu(z, 0.1)
+    pooled, am = F.max_pool2d(a, 2, 2, return_indices=True)
+    cnt = float(N * H * W)
+    # ---- device
+    xd = x.to(DEV)
+    wm = w.permute(0, 2, 3, 1).contiguous().to(DEV)                      # master layout [co][kh][kw][ci]
+    gram = torch.zeros(28 * 28, dtype=torch.float64, device=DEV)
+    ssum = torch.zeros(32, dtype=torch.float64, device=DEV); ssq = torch.zeros_like(ssum)
+    s = stream_ptr()
+    call("ssp_l0_gram", ptr(xd), N, H, W, ptr(gram), s)
+    call("ssp_l0_stats", ptr(gram), ptr(wm), ptr(ssum), ptr(ssq), s)
+    torch.cuda.synchronize()
+    # Gram matrix against the im2col'ed patches (k = (kh*3+kw)*3 + c)
+    P = F.unfold(x.double(), 3, padding=1).view(N, 3, 9, H * W).permute(0, 3, 2, 1).reshape(-1, 27)      # [px][tap][c]
+    Q = torch.cat([P, torch.ones(P.shape[0], 1, dtype=torch.float64)], dim=1)
+    Gref = Q.t() @ Q
+    G = gram.cpu().view(28, 28)
+    iu = torch.triu_indices(28, 28)
+    assert ((G[iu[0], iu[1]] - Gref[iu[0], iu[1]]).abs() / Gref[iu[0], iu[1]].abs().clamp_min(1.0)).max() < 2e-6
+    assert (ssum.cpu() - y.detach().sum(dim=(0, 2, 3))).abs().max() < 1e-5 * cnt
+    q_ref = (y.detach() ** 2).sum(dim=(0, 2, 3))
+    assert ((ssq.cpu() - q_ref).abs() / q_ref).max() < 2e-6
+    rm = torch.zeros(32, device=DEV); rv = torch.ones(32, device=DEV)
+    mean_d = torch.zeros(32, device=DEV); invstd_d = torch.zeros(32, device=DEV); scale_d = torch.zeros(32, device=DEV); shift_d = torch.zeros(32, device=DEV)
+    gamma_d, beta_d = gamma.to(DEV), beta.to(DEV)                          # named: a temporary would be freed (and its memory reused) before the launch
+    call("ssp_bn_finalize", ptr(ssum), ptr(ssq), cnt, ptr(gamma_d), ptr(beta_d), ptr(rm), ptr(rv), 0.1, eps, 1,
+         ptr(mean_d), ptr(invstd_d), ptr(scale_d), ptr(shift_d), 32, s)
+    assert (mean_d.cpu().double() - mean.detach()).abs().max() < 1e-6
+    assert ((invstd_d.cpu().double() - 1.0 / torch.sqrt(var.detach() + eps)).abs() * torch.sqrt(var.detach() + eps)).max() < 1e-5
+    prow = _lib.flat_alloc_rows(N, H // 2, W // 2)
+    ld, c0 = 40, 4                                                       # destination wider than the layer: concat placement
+    hi = torch.zeros(prow, ld, dtype=torch.float16, device=DEV); lo = torch.zeros_like(hi)
+    code = torch.full((prow, 32), 255, dtype=torch.uint8, device=DEV)
+    call("ssp_l0_fused_fwd", ptr(xd), ptr(wm), ptr(scale_d), ptr(shift_d), 0.1, N, H, W, ptr(hi), ptr(lo), ld, c0, ptr(code), s)
+    torch.cuda.synchronize()
+    idx = torch_flat_index(N, H // 2, W // 2)
+    got = (hi.float() + lo.float()).cpu()[idx][:, c0:c0 + 32].reshape(N, H // 2, W // 2, 32).permute(0, 3, 1, 2)
+    assert (got.double() - pooled.detach()).abs().max() / pooled.detach().abs().max() < 2e-5
+    v = (hi.float() + lo.float()).cpu()
+    mask = torch.ones(prow, dtype=torch.bool); mask[idx] = False
+    assert float(v[mask].abs().max()) == 0.0 and float(v[:, :c0].abs().max()) == 0.0 and float(v[:, c0 + 32:].abs().max()) == 0.0
+    # arg-max codes: position inside the window and the sign of the pre-activation there.  fp32-vs-fp64 rounding may pick the other
+    # element of an (almost exact) tie: the selected VALUE must be the maximum, the position may differ on a vanishing fraction
+    cd = code.cpu()[idx].reshape(N, H // 2, W // 2, 32).permute(0, 3, 1, 2).long()
+    hh = torch.arange(H // 2).view(1, 1, -1, 1) * 2 + ((cd >> 1) & 1); ww = torch.arange(W // 2).view(1, 1, 1, -1) * 2 + (cd & 1)
+    pos = hh * W + ww
+    a_sel = a.detach().flatten(2).gather(2, pos.flatten(2)).view_as(pos)
+    assert (a_sel - pooled.detach()).abs().max() < 1e-5 * pooled.detach().abs().max()
+    assert float((pos != am).float().mean()) < 1e-3
+    zsel = z.detach().flatten(2).gather(2, pos.flatten(2)).view_as(pos)
+    sure = zsel.abs() > 1e-5
+    assert torch.equal(((cd & 4) != 0)[sure], (zsel > 0)[sure])
+    # reference backward routed through the device's arg-max positions (a valid subgradient; identical unless there was a tie)
+    (a.flatten(2).gather(2, pos.flatten(2)).view_as(pos) * gpool.double()).sum().backward()
+    assert int(code.cpu()[mask].min()) == 255                             # pad cells untouched
+    # ---- backward from the pooled gradient (loss scale 256 carried like the engine does)
+    gflat = torch.zeros(prow, ld, device=DEV)
+    gflat[idx.to(DEV), c0:c0 + 32] = (gpool * 256.0).permute(0, 2, 3, 1).reshape(-1, 32).to(DEV)
+    t1 = torch.zeros(28 * 32, dtype=torch.float64, device=DEV)
+    dW = torch.zeros(32, 27, device=DEV); dga = torch.zeros(32, device=DEV); dbe = torch.zeros(32, device=DEV)
+    call("ssp_l0_bwd", ptr(xd), ptr(gflat), ld, c0, ptr(code), 0.1, N, H, W, ptr(t1), s)
+    call("ssp_l0_bwd_finalize", ptr(t1), ptr(gram), ptr(wm), ptr(gamma_d), ptr(mean_d), ptr(invstd_d), cnt, 1.0 / 256.0,
+         ptr(dW), ptr(dga), ptr(dbe), s)
+    torch.cuda.synchronize()
+    dW_ref = wd.grad.permute(0, 2, 3, 1).reshape(32, 27)
+    assert (dW.cpu().double() - dW_ref).abs().max() / dW_ref.abs().max() < 1e-4
+    assert (dga.cpu().double() - gd.grad).abs().max() / gd.grad.abs().max() < 1e-4
+    assert (dbe.cpu().double() - bd.grad).abs().max() / bd.grad.abs().max() < 1e-4
+
+
+BANDT_FWD = [
+    # N, H, W, cin, cout, k   (split-fp16 forward with BN statistics; cout <= 64: W_hi / W_lo stacked on the M side)
+    (2, 40, 24, 32, 64, 3),        # block-2 class: 128-pixel tiles (nine resident 16 KB tiles leave room for two 136-row bands only)
+    (4, 104, 104, 32, 64, 3),      # 345 tiles: several tiles per CTA, both TMEM buffers and every ring phase in use
+    (2, 26, 26, 128, 64, 1),       # 1x1, two K chunks, 256-pixel tiles
+    (3, 5, 7, 64, 32, 3),          # cout 32: half of each stacked plane is zero fill
+    (1, 13, 13, 64, 24, 3),        # cout not a multiple of 32
+]
+BANDT_DGRAD = [
+    # N, H, W, channels of dY (K per tap), channels of dX (<= 128), k      (single-term fp16)
+    (2, 40, 24, 64, 32, 3),        # block-2 data gradient: 32 of the 128 TMEM lanes carry output
+    (4, 104, 104, 64, 32, 3),
+    (2, 26, 26, 128, 64, 3),       # block-3/5 data gradient
+    (2, 13, 13, 64, 128, 3),
+    (2, 26, 26, 64, 128, 1),
+]
+
+
+@pytest.mark.parametrize("case", BANDT_FWD)
+def test_conv_bandt_forward_runs_and_matches_torch(case):
+    """operand-swapped kernel (csrc/conv_bandt.cu): the kernel itself must have run (launch counter), outputs / BN statistics
+    against the fp64 torch convolution at the tolerance of the other tensor-core kernels."""
+    N, H, W, cin, cout, k = case
+    g = torch.Generator().manual_seed(31 + cin + cout + H)
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    ref = F.conv2d(x.double(), w.double(), None, padding=(k - 1) // 2).float()
+    xh, xl, rows = flat_from_nchw(x.to(DEV))
+    wh, wl, _ = _pack_w(w.to(DEV))
+    ldo = (cout + 3) // 4 * 4
+    y = torch.full((rows, ldo), float("nan"), device=DEV)
+    ssum = torch.zeros(cout, dtype=torch.float64, device=DEV); ssq = torch.zeros_like(ssum)
+    before = _lib.load().ssp_conv_bandt_launches()
+    call("ssp_conv_gemm", _lib.IMPL_BANDT, ptr(xh), ptr(xl), rows, cin, cin, ptr(wh), ptr(wl), cout, wh.shape[1], 0, 0,
+         N, H, W, k * k, cout, ptr(y), ldo, rows, _lib.EPI_STATS, None, ptr(ssum), ptr(ssq), stream_ptr())
+    torch.cuda.synchronize()
+    assert _lib.load().ssp_conv_bandt_launches() == before + 1
+    out = nchw_from_flat(y, N, cout, H, W).cpu()
+    tol = 2e-5 + 5e-9 * cin * k * k
+    assert (out - ref).abs().max() / ref.abs().max() < tol
+    s_ref = ref.double().sum(dim=(0, 2, 3)); q_ref = (ref.double() ** 2).sum(dim=(0, 2, 3))
+    assert (ssum.cpu() - s_ref).abs().max() < 1e-4 * q_ref.max().sqrt() * (N * H * W) ** 0.5
+    assert ((ssq.cpu() - q_ref).abs() / q_ref).max() < 1e-4
+
+
+@pytest.mark.parametrize("case", BANDT_DGRAD)
+def test_conv_bandt_dgrad_runs_and_matches_torch(case):
+    N, H, W, cy, cx, k = case
+    g = torch.Generator().manual_seed(7 + cy + cx + H)
+    dy = torch.randn(N, cy, H, W, generator=g)
+    w = torch.randn(cy, cx, k, k, generator=g) / (cy * k * k) ** 0.5         # forward weight OIHW: cy = cout, cx = cin
+    dyq = dy.half().float(); wq = w.half().float()
+    ref = F.conv_transpose2d(dyq.double(), wq.double(), padding=(k - 1) // 2).float()
+    dyh, _, rows = flat_from_nchw(dy.to(DEV), fmt=_lib.FMT_F16, split=False)
+    _, _, wd = _pack_w(w.to(DEV), fmt=_lib.FMT_F16, dgrad=True)
+    dx = torch.full((rows, cx), float("nan"), device=DEV)
+    before = _lib.load().ssp_conv_bandt_launches()
+    call("ssp_conv_gemm", _lib.IMPL_BANDT, ptr(dyh), None, rows, cy, cy, ptr(wd), None, cx, wd.shape[1], 0, 0,
+         N, H, W, k * k, cx, ptr(dx), cx, rows, _lib.EPI_F32, None, None, None, stream_ptr())
+    torch.cuda.synchronize()
+    assert _lib.load().ssp_conv_bandt_launches() == before + 1
+    out = nchw_from_flat(dx, N, cx, H, W).cpu()
+    assert (out - ref).abs().max() / ref.abs().max() < 1e-4

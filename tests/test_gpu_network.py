@@ -267,18 +267,20 @@ def test_fused_sgd_repack_and_bucketed_step_match_plain(cfg_path, monkeypatch):
             if it == 0:
                 first = [p.detach().clone() for p in m.parameters()]
         outs.append((logits, first, [p.detach().clone() for p in m.parameters()]))
-    # Step 2 re-amplifies the 1e-7 weight differences that the fp32 atomics' summation order leaves after step 1 (chaotic net):
-    # parameters that start at zero (BN beta, the head's bias) are pure sums of gradients after two steps, so their relative
-    # difference IS the gradient noise.  The floor is measured here -- plain vs plain -- instead of guessed (B200, round 2: a
-    # fixed 2e-3 failed at 4.4e-3 on a bias of magnitude 3e-5).
-    floor = [_rel(p, q) for p, q in zip(outs[1][2], outs[0][2])]
+    # Step 2 re-amplifies the 1e-7 weight differences that the fp32 atomics' summation order leaves after step 1 (chaotic net).
+    # Parameters that start at zero (BN beta, biases) are pure sums of gradients after two steps, so their relative difference IS
+    # the step-2 gradient noise: bounded like the gradient-parity tests (5e-2; on B200 the plain path against ITSELF gives 3e-3 ...
+    # 2e-2 on a beta of magnitude 3e-5, measured here and printed).  Everything else moves by lr * grad << its own size: 2e-3.
+    floor = max(_rel(p, q) for p, q in zip(outs[1][2], outs[0][2]))
+    print("plain-vs-plain step-2 noise floor (max over tensors): %.2e" % floor)
     for logits, first, params in outs[2:]:
         assert torch.equal(logits[0], outs[0][0][0])
         for p, q in zip(first, outs[0][1]):
             assert _rel(p, q) < 1e-6                          # one step: the same update up to the atomics' summation order
         assert _rel(logits[1], outs[0][0][1]) < 1e-4          # second forward used the planes the optimiser wrote
-        for p, q, fl in zip(params, outs[0][2], floor):
-            assert _rel(p, q) < max(2e-3, 4.0 * fl) and _rel(p, q) < 5e-2
+        for p, q, p0 in zip(params, outs[0][2], base.parameters()):
+            zero_init = float(p0.detach().abs().max()) == 0.0
+            assert _rel(p, q) < (5e-2 if zero_init else 2e-3)
 
 
 def _grad_errors(model_params, ref_params):
