@@ -38,10 +38,12 @@ extern "C" {
 #define SSP_EPI_F32 0    /* store fp32 */
 #define SSP_EPI_STATS 1  /* store fp32 + per-channel sum / sum of squares over valid pixels (fp64) */
 #define SSP_EPI_BIAS 2   /* add bias, store fp32 */
+#define SSP_EPI_F16 8    /* store fp16 (saturating): `out` points to 16-bit elements, out_ld in elements; data gradients only (TC2 / BANDT kernels) */
 #define SSP_ROUTE_NONE 0
 #define SSP_ROUTE_DIRECT 1 /* consumer has the same geometry */
 #define SSP_ROUTE_POOL 2   /* consumer is behind MaxPool2d(2,2)          (darknet.py:168-176) */
 #define SSP_ROUTE_REORG 3  /* consumer is behind Reorg(2), marvis order  (darknet.py:16-35)   */
+#define SSP_ROUTE_F16 16   /* OR-ed into a g*_route of ssp_bn_bwd_*: that upstream gradient plane holds fp16 (written with SSP_EPI_F16) instead of fp32 */
 
 int ssp_version(void);
 const char* ssp_last_error(void);              /* host pointer, thread-local text of the last failure */
@@ -85,8 +87,8 @@ int ssp_l0_gram(const float* x_nchw, int N, int H, int W, double* gram, void* st
 int ssp_l0_stats(const double* gram, const float* w, double* stat_sum, double* stat_sq, void* stream);
 int ssp_l0_fused_fwd(const float* x_nchw, const float* w, const float* scale, const float* shift, float slope, int N, int H, int W,
                      void* d_hi, void* d_lo, int d_ld, int d_c0, unsigned char* code_or_null, void* stream);
-int ssp_l0_bwd(const float* x_nchw, const float* g_pooled, int g_ld, int g_c0, const unsigned char* code, float slope, int N, int H,
-               int W, double* t1, void* stream);
+int ssp_l0_bwd(const float* x_nchw, const void* g_pooled, int g_f16, int g_ld, int g_c0, const unsigned char* code, float slope, int N,
+               int H, int W, double* t1, void* stream);   /* g_f16: the pooled gradient plane holds fp16 (SSP_EPI_F16) instead of fp32 */
 int ssp_l0_bwd_finalize(const double* t1, const double* gram, const float* w, const float* gamma, const float* mean,
                         const float* invstd, double count, float grad_scale, float* dw, float* dgamma, float* dbeta, void* stream);
 /* ---- nn.Conv2d weight gradient: dW[co][tap][ci] += scale * sum_m dY[m][co] * X[m + shift(tap)][ci] ---- */

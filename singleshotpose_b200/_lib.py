@@ -10,8 +10,9 @@ LIB_PATH = os.environ.get("SSP_LIB") or os.path.join(_HERE, "csrc", "libssp_b200
 
 FMT_F16, FMT_BF16 = 0, 1
 IMPL_TC, IMPL_SIMT, IMPL_TC2, IMPL_BAND, IMPL_BANDT = 0, 1, 2, 3, 4
-EPI_F32, EPI_STATS, EPI_BIAS = 0, 1, 2
+EPI_F32, EPI_STATS, EPI_BIAS, EPI_F16 = 0, 1, 2, 8
 ROUTE_NONE, ROUTE_DIRECT, ROUTE_POOL, ROUTE_REORG = 0, 1, 2, 3
+ROUTE_F16 = 16          # OR-ed into a gradient route of ssp_bn_bwd_*: that plane holds fp16
 
 _p, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 
@@ -31,7 +32,7 @@ SIGNATURES = {
     "ssp_l0_gram": [_p, _i, _i, _i, _p, _p],
     "ssp_l0_stats": [_p, _p, _p, _p, _p],
     "ssp_l0_fused_fwd": [_p, _p, _p, _p, _f, _i, _i, _i, _p, _p, _i, _i, _p, _p],
-    "ssp_l0_bwd": [_p, _p, _i, _i, _p, _f, _i, _i, _i, _p, _p],
+    "ssp_l0_bwd": [_p, _p, _i, _i, _i, _p, _f, _i, _i, _i, _p, _p],
     "ssp_l0_bwd_finalize": [_p, _p, _p, _p, _p, _p, _d, _f, _p, _p, _p, _p],
     "ssp_conv_gemm_bnact": [_i, _p, _p, _ll, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _i, _i, _p],
     "ssp_wgrad_gemm": [_i, _p, _ll, _i, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _f, _p],

@@ -28,7 +28,7 @@ int conv0_direct(const float*, const float*, const float*, float*, int, double*,
 int l0_gram(const float*, int, int, int, double*, cudaStream_t);
 int l0_stats(const double*, const float*, double*, double*, cudaStream_t);
 int l0_fused_fwd(const float*, const float*, const float*, const float*, float, int, int, int, void*, void*, int, int, uint8_t*, cudaStream_t);
-int l0_bwd(const float*, const float*, int, int, const uint8_t*, float, int, int, int, double*, cudaStream_t);
+int l0_bwd(const float*, const void*, int, int, int, const uint8_t*, float, int, int, int, double*, cudaStream_t);
 int l0_bwd_finalize(const double*, const double*, const float*, const float*, const float*, const float*, double, float, float*, float*, float*, cudaStream_t);
 int wgrad_gemm_tc(const void*, long long, int, int, int, const void*, long long, int, int, int, int, int, int, int, float*, int, int, float, cudaStream_t);
 int wgrad_gemm_simt(const void*, long long, int, int, int, const void*, long long, int, int, int, int, int, int, int, float*, int, int, float, cudaStream_t);
@@ -87,6 +87,14 @@ int ssp_unpack16_nchw(const void* hi, const void* lo, float* out, int N, int C, 
 int ssp_conv_gemm(int impl, const void* a_hi, const void* a_lo, long long a_rows, int a_ld, int cin, const void* b_hi, const void* b_lo,
                   int b_rows, int b_ld, int a_fmt, int b_fmt, int N, int H, int W, int taps, int cout, float* out, int out_ld,
                   long long out_rows, int epi, const float* bias, double* ssum, double* ssq, void* s) {
+  if (epi == SSP_EPI_F16) {          // fp16 data-gradient planes: the operand-swapped kernel where eligible, the CTA-pair kernel otherwise
+    if (impl != SSP_IMPL_BANDT && impl != SSP_IMPL_TC2) return fail_msg(SSP_ERR_ARG, "ssp_conv_gemm: SSP_EPI_F16 needs SSP_IMPL_BANDT or SSP_IMPL_TC2");
+    if (impl == SSP_IMPL_BANDT) {
+      const int rc = conv_gemm_bandt(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
+      if (rc != 1) return rc;
+    }
+    return conv_gemm_tc2(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s), nullptr);
+  }
   if (impl == SSP_IMPL_SIMT)
     return conv_gemm_simt(a_hi, a_lo, a_rows, a_ld, cin, b_hi, b_lo, b_rows, b_ld, a_fmt, b_fmt, N, H, W, taps, cout, out, out_ld, out_rows, epi, bias, ssum, ssq, ST(s));
   if (impl == SSP_IMPL_BANDT) {
@@ -112,8 +120,8 @@ int ssp_l0_fused_fwd(const float* x, const float* w, const float* scale, const f
                      void* d_lo, int d_ld, int d_c0, unsigned char* code, void* s) {
   return l0_fused_fwd(x, w, scale, shift, slope, N, H, W, d_hi, d_lo, d_ld, d_c0, code, ST(s));
 }
-int ssp_l0_bwd(const float* x, const float* g, int g_ld, int g_c0, const unsigned char* code, float slope, int N, int H, int W, double* t1, void* s) {
-  return l0_bwd(x, g, g_ld, g_c0, code, slope, N, H, W, t1, ST(s));
+int ssp_l0_bwd(const float* x, const void* g, int g_f16, int g_ld, int g_c0, const unsigned char* code, float slope, int N, int H, int W, double* t1, void* s) {
+  return l0_bwd(x, g, g_f16, g_ld, g_c0, code, slope, N, H, W, t1, ST(s));
 }
 int ssp_l0_bwd_finalize(const double* t1, const double* gram, const float* w, const float* gamma, const float* mean, const float* invstd,
                         double count, float gscale, float* dw, float* dgamma, float* dbeta, void* s) {

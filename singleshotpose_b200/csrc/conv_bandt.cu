@@ -198,7 +198,15 @@ __global__ void __launch_bounds__(kThreadsT, 1) conv_bandt_kernel(const __grid_c
               // branch-free inner loops: a predicated store per element compiles to a BSSY / BRA / BSYNC triple per column and the
               // epilogue, not the tensor pipe, bounded the kernel (round 2, ncu: 2k clk per 32-column chunk, 28 % tensor active)
               float* o = p.out + (m0 + ch * 32) * p.out_ld + n_own;
-              if (m0 + ch * 32 + 32 <= p.store_rows) {
+              if (p.epi == EPI_F16) {                  // fp16 data gradient: the warp writes 64 B of every pixel row
+                uint16_t* o16 = reinterpret_cast<uint16_t*>(p.out) + (m0 + ch * 32) * p.out_ld + n_own;
+                if (m0 + ch * 32 + 32 <= p.store_rows) {
+#pragma unroll
+                  for (int j = 0; j < 32; j++) { *o16 = cvt_f32_to_16(__uint_as_float(r[j]), FMT_F16); o16 += p.out_ld; }
+                } else {
+                  for (int j = 0; j < 32; j++) if (m0 + ch * 32 + j < p.store_rows) o16[(long long)j * p.out_ld] = cvt_f32_to_16(__uint_as_float(r[j]), FMT_F16);
+                }
+              } else if (m0 + ch * 32 + 32 <= p.store_rows) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) { *o = __uint_as_float(r[j]); o += p.out_ld; }
               } else {
@@ -276,6 +284,7 @@ int conv_gemm_bandt(const void* a_hi, const void* a_lo, long long a_rows, int a_
   Geom g{N, H, W};
   p.stacked = (a_lo && b_lo) ? 1 : 0;
   if (p.stacked ? cout > 64 : cout > 128) return 1;
+  if (epi == EPI_F16 && p.stacked) return 1;
   if (a_fmt != b_fmt) return 1;
   const int planes = p.stacked ? 2 : 1;
   p.taps = taps; p.nk = taps == 9 ? 3 : 1;

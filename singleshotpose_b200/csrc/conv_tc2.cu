@@ -265,7 +265,21 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
 #pragma unroll
           for (int j = 0; j < 32; j++) if (c0 + j < p.cout) v[j] += __ldg(p.bias + c0 + j);
         }
-        if (can_store && p.ksplit > 1) {            // split K: partial sums of the ksplit work items meet in the (pre-zeroed) output
+        if (p.epi == EPI_F16) {                     // data gradient kept in fp16 (the BN backward reads it twice): 64 B per row chunk
+          if (can_store) {
+            uint16_t* o16 = reinterpret_cast<uint16_t*>(p.out) + m * p.out_ld + c0;
+            if (c0 + 32 <= p.cout) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; j++) pk[j] = cvt_f32_to_16(v[2 * j], FMT_F16) | ((uint32_t)cvt_f32_to_16(v[2 * j + 1], FMT_F16) << 16);
+#pragma unroll
+              for (int j = 0; j < 4; j++) reinterpret_cast<uint4*>(o16)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++) if (c0 + j < p.cout) o16[j] = cvt_f32_to_16(v[j], FMT_F16);
+            }
+          }
+        } else if (can_store && p.ksplit > 1) {            // split K: partial sums of the ksplit work items meet in the (pre-zeroed) output
           if (c0 + 32 <= p.cout) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -329,7 +343,8 @@ int conv_gemm_tc2(const void* a_hi, const void* a_lo, long long a_rows, int a_ld
   if ((a_ld % 8) || (b_ld % 8)) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc2: leading dimensions must be multiples of 8 elements (16 B)");
   if (epi == EPI_STATS && (cout > kAccCols || !stat_sum || !stat_sq)) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc2: statistics need cout <= 1024 and buffers");
   if (epi == EPI_BIAS && !bias) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc2: bias missing");
-  if (!fa && ((out_ld % 4) || ((uintptr_t)out % 16))) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc2: output must be 16-B aligned with ld % 4 == 0");
+  if (!fa && epi != EPI_F16 && ((out_ld % 4) || ((uintptr_t)out % 16))) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc2: output must be 16-B aligned with ld % 4 == 0");
+  if (epi == EPI_F16 && ((out_ld % 8) || ((uintptr_t)out % 16))) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc2: fp16 output must be 16-B aligned with ld % 8 == 0");
   if (!g_num_sms2) {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms2, cudaDevAttrMultiProcessorCount, dev);

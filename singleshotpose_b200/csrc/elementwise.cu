@@ -268,7 +268,15 @@ __global__ void SSP_BN_BOUNDS bn_apply_kernel(const BnApplyParams p) {
 //   pass 1 (reduce): per-channel  S1 = sum dz,  S2 = sum dz * xhat          (fp64 atomics, one per block/channel)
 //   pass 2 (apply):  dY = gamma*invstd * (dz - S1/cnt - xhat*S2/cnt)  -> 16-bit plane (operand of dgrad/wgrad)
 enum { SRC_NONE = 0, SRC_DIRECT = 1, SRC_POOL = 2, SRC_REORG = 3 };
-struct GradSrc { const float* g; int ld, c0, kind; };
+struct GradSrc { const float* g; int ld, c0, kind, f16; };   // f16: the plane holds fp16 (written by a GEMM with EPI_F16), ld / c0 in elements
+__device__ __forceinline__ float4 load_grad4(const GradSrc& gs, long long elem) {
+  if (gs.f16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(gs.g) + elem);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(gs.g + elem);
+}
 struct BnBwdParams {
   const float* y; int y_ld;
   const float* scale; const float* shift; const float* mean; const float* invstd; const float* gamma;
@@ -314,9 +322,9 @@ struct BwdUnit {
         const GradSrc& gs = p.src[s];
         const int kind = s == 0 ? K0 : K1;                 // compile-time: unused sources cost no registers
         gd[s][q] = make_float4(0, 0, 0, 0);
-        if (kind == SRC_DIRECT) gd[s][q] = *reinterpret_cast<const float4*>(gs.g + rows[q] * gs.ld + gs.c0 + c);
+        if (kind == SRC_DIRECT) gd[s][q] = load_grad4(gs, rows[q] * gs.ld + gs.c0 + c);
         else if (kind == SRC_REORG)
-          gd[s][q] = *reinterpret_cast<const float4*>(gs.g + gh.row(n, h >> 1, w >> 1) * gs.ld + gs.c0 + ((h & 1) * 2 + (w & 1)) * p.C + c);
+          gd[s][q] = load_grad4(gs, gh.row(n, h >> 1, w >> 1) * gs.ld + gs.c0 + ((h & 1) * 2 + (w & 1)) * p.C + c);
       }
     }
 #pragma unroll
@@ -324,7 +332,7 @@ struct BwdUnit {
       const int kind = s == 0 ? K0 : K1;
       gp[s] = make_float4(0, 0, 0, 0);
       if (kind == SRC_POOL)
-        gp[s] = *reinterpret_cast<const float4*>(p.src[s].g + gh.row(n, hs, ws) * p.src[s].ld + p.src[s].c0 + c);
+        gp[s] = load_grad4(p.src[s], gh.row(n, hs, ws) * p.src[s].ld + p.src[s].c0 + c);
     }
   }
   // dz = (routed upstream gradient) * leaky'(z);  xh = normalised conv output
@@ -594,8 +602,8 @@ static int fill_bwd(BnBwdParams& p, const float* y, int y_ld, const float* scale
   p.y = y; p.y_ld = y_ld; p.scale = scale; p.shift = shift; p.mean = mean; p.invstd = invstd; p.gamma = gamma;
   p.has_bn = (scale && shift && mean && invstd && gamma) ? 1 : 0;
   p.N = N; p.C = C; p.H = H; p.W = W; p.slope = slope;
-  p.src[0] = GradSrc{g0, g0_ld, g0_c0, g0_kind};
-  p.src[1] = GradSrc{g1, g1_ld, g1_c0, g1 ? g1_kind : SRC_NONE};
+  p.src[0] = GradSrc{g0, g0_ld, g0_c0, g0_kind & 15, (g0_kind & SSP_ROUTE_F16) ? 1 : 0};
+  p.src[1] = GradSrc{g1, g1_ld, g1_c0, g1 ? (g1_kind & 15) : SRC_NONE, (g1_kind & SSP_ROUTE_F16) ? 1 : 0};
   p.s1 = s1; p.s2 = s2; p.count = (double)N * H * W;
   p.dy = nullptr; p.dy_ld = 0; p.dy_fmt = 0; p.dy_scale = 1.f;
   return SSP_OK;

@@ -28,7 +28,7 @@ int fail_msg(int code, const char* msg);
 
 enum Fmt16 { FMT_F16 = 0, FMT_BF16 = 1 };
 // GEMM epilogues: plain fp32 store | store + per-channel sum / sum-of-squares over valid pixels | + bias
-enum { EPI_F32 = 0, EPI_STATS = 1, EPI_BIAS = 2, EPI_BNACT = 4 };
+enum { EPI_F32 = 0, EPI_STATS = 1, EPI_BIAS = 2, EPI_BNACT = 4, EPI_F16 = 8 };
 // inference-mode fusion: z = leaky(acc*scale[c] + shift[c]) written straight into the consumer's fp16 hi/lo operand planes
 struct FusedAct {
   const float* scale; const float* shift; float slope;

@@ -162,7 +162,8 @@ class Buffers:
                 # plane + the pooled gradient (8 B per window) instead of the four full-resolution y values + the gradient (20 B)
                 self.ypool.append(torch.zeros(_lib.flat_alloc_rows(N, h // 2, w // 2), _rup(L.cout, 4), dtype=torch.float32, device=dev) if pooled else None)
                 self.dy.append(torch.zeros(rows, _rup(L.cout, 8), dtype=eng.grad_dtype, device=dev))
-                self.dx.append(None if L.first else torch.zeros(rows, cin_total, dtype=torch.float32, device=dev))
+                self.dx.append(None if L.first else torch.zeros(rows, _rup(cin_total, 8) if eng.dx_f16 else cin_total,
+                                                                dtype=torch.float16 if eng.dx_f16 else torch.float32, device=dev))
 
 
 class Engine:
@@ -194,6 +195,10 @@ class Engine:
         self.grad_scale = float(os.environ.get("SSP_GRAD_SCALE", "256"))
         self.grad_dtype = torch.float16 if self.grad_fmt == _lib.FMT_F16 else torch.bfloat16
         self.fast = os.environ.get("SSP_PRECISION", "parity").lower() == "fast"   # single-term forward (no hi/lo)
+        # data gradients dX kept in fp16 (loss-scaled, saturating) instead of fp32: the BN backward reads every dX twice, the GEMM
+        # epilogue writes it once -- 6 of the ~22 bytes per activation element of the backward pass.  Needs the kernels that have the
+        # fp16 epilogue (auto dispatch: CTA-pair / operand-swapped); forced implementations keep fp32 planes.
+        self.dx_f16 = os.environ.get("SSP_DX_F16", "1") != "0" and self.conv_impl < 0 and self.grad_fmt == _lib.FMT_F16
         self.launches = 0
         self.overlap = os.environ.get("SSP_OVERLAP", "1") != "0"
         self.compact_pool_reduce = os.environ.get("SSP_POOL_REDUCE", "compact") != "full"
@@ -535,7 +540,7 @@ class Engine:
                     ev = torch.cuda.Event()
                     ev.record(main)
                     side.wait_event(ev)
-                self._gemm("wgrad", L, N, h, w, "ssp_l0_bwd", ptr(B.x_image), ptr(B.dx[ci]), B.dx[ci].shape[1], c0, ptr(B.l0_code), L.slope,
+                self._gemm("wgrad", L, N, h, w, "ssp_l0_bwd", ptr(B.x_image), ptr(B.dx[ci]), 1 if self.dx_f16 else 0, B.dx[ci].shape[1], c0, ptr(B.l0_code), L.slope,
                            N, H, W, ptr(B.l0_t1), ws, stream=wstream)
                 call("ssp_l0_bwd_finalize", ptr(B.l0_t1), ptr(B.l0_gram), ptr(self.flat_params[off:off + n]), ptr(bn.weight.data),
                      ptr(st["mean"]), ptr(st["invstd"]), float(N * h * w), inv, ptr(self.flat_grads[off:off + n]),
@@ -546,8 +551,9 @@ class Engine:
                 continue
             if L.bn:
                 srcs = []
+                f16 = _lib.ROUTE_F16 if self.dx_f16 else 0
                 for (ci, c0, kind) in L.dests:
-                    srcs += [ptr(B.dx[ci]), B.dx[ci].shape[1], c0, kind]
+                    srcs += [ptr(B.dx[ci]), B.dx[ci].shape[1], c0, kind | f16]
                 if len(L.dests) == 1:
                     srcs += [None, 0, 0, _lib.ROUTE_NONE]
                 common = [ptr(B.y[i]), B.y[i].shape[1], ptr(st["scale"]), ptr(st["shift"]), ptr(st["mean"]), ptr(st["invstd"]),
@@ -561,9 +567,9 @@ class Engine:
                     for (ci, c0, kind) in L.dests:
                         if kind == _lib.ROUTE_POOL:
                             call("ssp_bn_bwd_reduce", ptr(yp), yp.shape[1], *head[2:], N, L.cout, h // 2, w // 2, L.slope,
-                                 ptr(B.dx[ci]), B.dx[ci].shape[1], c0, _lib.ROUTE_DIRECT, None, 0, 0, _lib.ROUTE_NONE, ptr(st["s1"]), ptr(st["s2"]), s)
+                                 ptr(B.dx[ci]), B.dx[ci].shape[1], c0, _lib.ROUTE_DIRECT | f16, None, 0, 0, _lib.ROUTE_NONE, ptr(st["s1"]), ptr(st["s2"]), s)
                         else:
-                            call("ssp_bn_bwd_reduce", *head, N, L.cout, h, w, L.slope, ptr(B.dx[ci]), B.dx[ci].shape[1], c0, kind,
+                            call("ssp_bn_bwd_reduce", *head, N, L.cout, h, w, L.slope, ptr(B.dx[ci]), B.dx[ci].shape[1], c0, kind | f16,
                                  None, 0, 0, _lib.ROUTE_NONE, ptr(st["s1"]), ptr(st["s2"]), s)
                         self.launches += 1
                     self.launches -= 1
@@ -585,9 +591,12 @@ class Engine:
                 ev.record(main)                      # dY of this layer is complete
             if not L.first:                          # data gradient first: it is on the critical path of the next layer
                 wd = self.w_d[i]
-                self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm", self._conv_impl(L.cin, L.taps, 1), ptr(dy), None, B.rows[i], dy.shape[1], L.cout,
+                dimpl = self._conv_impl(L.cin, L.taps, 1)
+                if self.dx_f16 and dimpl not in (_lib.IMPL_BANDT, _lib.IMPL_TC2):
+                    dimpl = _lib.IMPL_TC2          # the kernels that have the fp16 epilogue
+                self._gemm("dgrad", L, N, h, w, "ssp_conv_gemm", dimpl, ptr(dy), None, B.rows[i], dy.shape[1], L.cout,
                            ptr(wd), None, L.cin, wd.shape[1], self.grad_fmt, self.grad_fmt, N, h, w, L.taps, L.cin, ptr(B.dx[i]),
-                           B.dx[i].shape[1], B.rows[i], _lib.EPI_F32, None, None, None, s)
+                           B.dx[i].shape[1], B.rows[i], _lib.EPI_F16 if self.dx_f16 else _lib.EPI_F32, None, None, None, s)
             if overlap:
                 side.wait_event(ev)
             if L.first:

@@ -242,9 +242,10 @@ def _bn_ref(y, gamma, beta, route):
     return z
 
 
+@pytest.mark.parametrize("gf16", [False, True])               # upstream gradient plane in fp32, or in fp16 as a GEMM with SSP_EPI_F16 writes it
 @pytest.mark.parametrize("route", [_lib.ROUTE_DIRECT, _lib.ROUTE_POOL, _lib.ROUTE_REORG])
 @pytest.mark.parametrize("C", [32, 256])
-def test_bn_apply_and_backward(route, C):
+def test_bn_apply_and_backward(route, C, gf16):
     N, H, W = 3, 8, 6
     g = torch.Generator().manual_seed(11)
     y = (torch.randn(N, C, H, W, generator=g) * 1.7 + 0.3).requires_grad_(True)
@@ -253,6 +254,8 @@ def test_bn_apply_and_backward(route, C):
     beta = torch.randn(C, generator=g).requires_grad_(True)
     out_ref = _bn_ref(y, gamma, beta, route)
     gup = torch.randn(out_ref.shape, generator=g)
+    if gf16:
+        gup = gup.half().float()                               # the reference sees the values the fp16 plane holds
     out_ref.backward(gup)
     # ---- device: statistics come from the conv epilogue in production; here computed by torch in fp64 ----
     yd = y.detach().to(DEV)
@@ -280,17 +283,18 @@ def test_bn_apply_and_backward(route, C):
     call("ssp_unpack16_nchw", ptr(ohi), ptr(olo), ptr(got), oN, oC, oH, oW, oC, 0, 0, stream_ptr())
     assert (got.cpu() - out_ref.detach()).abs().max() < 2e-5 * out_ref.detach().abs().max()
     # ---- backward ----
-    gf = torch.zeros(orows, oC, device=DEV)
-    gf[torch_flat_index(oN, oH, oW).to(DEV)] = gup.to(DEV).permute(0, 2, 3, 1).reshape(-1, oC)
+    gf = torch.zeros(orows, oC, dtype=torch.float16 if gf16 else torch.float32, device=DEV)
+    gf[torch_flat_index(oN, oH, oW).to(DEV)] = gup.to(DEV).permute(0, 2, 3, 1).reshape(-1, oC).to(gf.dtype)
+    gflag = _lib.ROUTE_F16 if gf16 else 0
     s1 = torch.zeros(C, dtype=torch.float64, device=DEV); s2 = torch.zeros_like(s1)
     common = [ptr(yf), C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(gm), N, C, H, W, 0.1,
-              ptr(gf), oC, 0, route, None, 0, 0, 0, ptr(s1), ptr(s2)]
+              ptr(gf), oC, 0, route | gflag, None, 0, 0, 0, ptr(s1), ptr(s2)]
     call("ssp_bn_bwd_reduce", *common, stream_ptr())
     if ypool is not None:
         # quarter-resolution first pass from the arg-max plane: the same S1 / S2 as the full-resolution reduction
         t1 = torch.zeros_like(s1); t2 = torch.zeros_like(s2)
         call("ssp_bn_bwd_reduce", ptr(ypool), C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(gm), N, C, H // 2, W // 2, 0.1,
-             ptr(gf), oC, 0, _lib.ROUTE_DIRECT, None, 0, 0, 0, ptr(t1), ptr(t2), stream_ptr())
+             ptr(gf), oC, 0, _lib.ROUTE_DIRECT | gflag, None, 0, 0, 0, ptr(t1), ptr(t2), stream_ptr())
         torch.cuda.synchronize()
         assert torch.allclose(t1, s1, rtol=1e-6, atol=1e-6 * float(s1.abs().max()))
         assert torch.allclose(t2, s2, rtol=1e-6, atol=1e-6 * float(s2.abs().max()))
@@ -421,7 +425,7 @@ def test_l0_fused_blocks_match_torch(shape):
     w = (torch.randn(32, 3, 3, 3, generator=g) * 0.3)
     gamma = torch.rand(32, generator=g) + 0.5
     beta = torch.randn(32, generator=g) * 0.2
-    gpool = torch.randn(N, 32, H // 2, W // 2, generator=g)
+    gpool = (torch.randn(N, 32, H // 2, W // 2, generator=g) * 256.0).half().float() / 256.0      # exactly representable in the loss-scaled fp16 plane
     # ---- reference: fp64 autograd
     wd = w.double().requires_grad_(True); gd = gamma.double().requires_grad_(True); bd = beta.double().requires_grad_(True)
     y = F.conv2d(x.double(), wd, padding=1)
@@ -484,11 +488,11 @@ def test_l0_fused_blocks_match_torch(shape):
     (a.flatten(2).gather(2, pos.flatten(2)).view_as(pos) * gpool.double()).sum().backward()
     assert int(code.cpu()[mask].min()) == 255                             # pad cells untouched
     # ---- backward from the pooled gradient (loss scale 256 carried like the engine does)
-    gflat = torch.zeros(prow, ld, device=DEV)
-    gflat[idx.to(DEV), c0:c0 + 32] = (gpool * 256.0).permute(0, 2, 3, 1).reshape(-1, 32).to(DEV)
+    gflat = torch.zeros(prow, ld, dtype=torch.float16, device=DEV)       # the engine's default: data gradients live in fp16 planes
+    gflat[idx.to(DEV), c0:c0 + 32] = (gpool * 256.0).permute(0, 2, 3, 1).reshape(-1, 32).to(DEV).half()
     t1 = torch.zeros(28 * 32, dtype=torch.float64, device=DEV)
     dW = torch.zeros(32, 27, device=DEV); dga = torch.zeros(32, device=DEV); dbe = torch.zeros(32, device=DEV)
-    call("ssp_l0_bwd", ptr(xd), ptr(gflat), ld, c0, ptr(code), 0.1, N, H, W, ptr(t1), s)
+    call("ssp_l0_bwd", ptr(xd), ptr(gflat), 1, ld, c0, ptr(code), 0.1, N, H, W, ptr(t1), s)
     call("ssp_l0_bwd_finalize", ptr(t1), ptr(gram), ptr(wm), ptr(gamma_d), ptr(mean_d), ptr(invstd_d), cnt, 1.0 / 256.0,
          ptr(dW), ptr(dga), ptr(dbe), s)
     torch.cuda.synchronize()
@@ -543,8 +547,9 @@ def test_conv_bandt_forward_runs_and_matches_torch(case):
     assert ((ssq.cpu() - q_ref).abs() / q_ref).max() < 1e-4
 
 
+@pytest.mark.parametrize("out16", [False, True])              # fp32 plane, or the fp16 plane of SSP_EPI_F16
 @pytest.mark.parametrize("case", BANDT_DGRAD)
-def test_conv_bandt_dgrad_runs_and_matches_torch(case):
+def test_conv_bandt_dgrad_runs_and_matches_torch(case, out16):
     N, H, W, cy, cx, k = case
     g = torch.Generator().manual_seed(7 + cy + cx + H)
     dy = torch.randn(N, cy, H, W, generator=g)
@@ -553,11 +558,32 @@ def test_conv_bandt_dgrad_runs_and_matches_torch(case):
     ref = F.conv_transpose2d(dyq.double(), wq.double(), padding=(k - 1) // 2).float()
     dyh, _, rows = flat_from_nchw(dy.to(DEV), fmt=_lib.FMT_F16, split=False)
     _, _, wd = _pack_w(w.to(DEV), fmt=_lib.FMT_F16, dgrad=True)
-    dx = torch.full((rows, cx), float("nan"), device=DEV)
+    dx = torch.full((rows, cx), float("nan"), dtype=torch.float16 if out16 else torch.float32, device=DEV)
     before = _lib.load().ssp_conv_bandt_launches()
     call("ssp_conv_gemm", _lib.IMPL_BANDT, ptr(dyh), None, rows, cy, cy, ptr(wd), None, cx, wd.shape[1], 0, 0,
-         N, H, W, k * k, cx, ptr(dx), cx, rows, _lib.EPI_F32, None, None, None, stream_ptr())
+         N, H, W, k * k, cx, ptr(dx), cx, rows, _lib.EPI_F16 if out16 else _lib.EPI_F32, None, None, None, stream_ptr())
     torch.cuda.synchronize()
     assert _lib.load().ssp_conv_bandt_launches() == before + 1
-    out = nchw_from_flat(dx, N, cx, H, W).cpu()
-    assert (out - ref).abs().max() / ref.abs().max() < 1e-4
+    out = nchw_from_flat(torch.nan_to_num(dx.float()).contiguous(), N, cx, H, W).cpu()
+    assert (out - ref).abs().max() / ref.abs().max() < (1e-3 if out16 else 1e-4)      # fp16 storage: 2^-11 relative per element
+
+
+@pytest.mark.parametrize("case", [(2, 13, 13, 256, 512, 3), (2, 26, 26, 128, 256, 1), (1, 13, 13, 96, 40, 3)])
+def test_conv_tc2_dgrad_fp16_plane(case):
+    """SSP_EPI_F16 of the CTA-pair kernel (csrc/conv_tc2.cu): the data gradient stored as fp16 equals the fp32 plane rounded once"""
+    N, H, W, cy, cx, k = case
+    g = torch.Generator().manual_seed(3 + cy)
+    dy = torch.randn(N, cy, H, W, generator=g)
+    w = torch.randn(cy, cx, k, k, generator=g) / (cy * k * k) ** 0.5
+    dyh, _, rows = flat_from_nchw(dy.to(DEV), fmt=_lib.FMT_F16, split=False)
+    _, _, wd = _pack_w(w.to(DEV), fmt=_lib.FMT_F16, dgrad=True)
+    ld16 = (cx + 7) // 8 * 8
+    d32 = torch.zeros(rows, (cx + 3) // 4 * 4, device=DEV); d16 = torch.zeros(rows, ld16, dtype=torch.float16, device=DEV)
+    for out, ld, epi in ((d32, d32.shape[1], _lib.EPI_F32), (d16, ld16, _lib.EPI_F16)):
+        call("ssp_conv_gemm", _lib.IMPL_TC2, ptr(dyh), None, rows, cy, cy, ptr(wd), None, cx, wd.shape[1], 0, 0,
+             N, H, W, k * k, cx, ptr(out), ld, rows, epi, None, None, None, stream_ptr())
+    torch.cuda.synchronize()
+    idx = torch_flat_index(N, H, W).to(DEV)
+    a = d32[idx][:, :cx]; b = d16[idx][:, :cx]
+    assert torch.equal(a.half(), b)
+    assert float(d16[:, cx:].abs().max()) == 0.0 if ld16 > cx else True
