@@ -34,7 +34,7 @@ namespace ssp {
 
 struct ConvTc2Params {
   CUtensorMap tmA[2];
-  CUtensorMap tmB[2];
+  CUtensorMap tmB[2];     // box rows = bn / 2 (clusters of one pair) or bn / 4 (clusters of two pairs: the weight tile is multicast)
   long long m_rows;       // rows of the output matrix that exist (N*(H+1)*(W+1))
   long long store_rows;   // rows that may be written (allocation bound)
   int m_tiles, n_tiles;
@@ -72,6 +72,13 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tma
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same, written into this CTA and the CTAs of `mask` at the same offset; every destination's pair leader is credited
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -81,13 +88,13 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, 
       : "memory");
 }
 // completion of all previously issued MMAs arrives on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
-               ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive_rank(uint64_t* bar, uint32_t target) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+               ::"r"(smem_u32(bar)), "r"(target) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
@@ -100,8 +107,20 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 // MODE 0: training / generic epilogues.  MODE 1: the inference epilogue (EPI_BNACT).  Separate instantiations keep MODE 0's
 // register budget.  (A MODE 2 that folded the BN-backward reduction of the producer into the data-gradient epilogue was measured
 // in round 2: 18.29 vs 18.13 ms/step, the extra Y reads sit on the dgrad critical path -- removed.)
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc2_kernel(const __grid_constant__ ConvTc2Params p) {
+// CSZ = CTAs per cluster: 2 = one CTA pair; 4 = two pairs on consecutive M tiles and the SAME N tile -- every CTA fetches half of its
+// half of the weight tile and multicasts it to its counterpart in the other pair.  Round 2, tools/probes/mc_probe2.cu: the operand
+// fill rate is bounded by what a CTA REQUESTS from L2 (64 B/clk/SM unicast with a deep queue, ~36-40 with the 224 KB a GEMM ring
+// can keep in flight) while an SM can take in 87-95 B/clk when the tiles arrive by multicast; a 256 x 256 single-term pair tile
+// needs 64 B/clk/SM at the full MMA rate, so the data / weight gradients sat at 62 % of the tensor pipe.  With the weight tile
+// shared the requested bytes per k-block drop from 32 KB to 24 KB per CTA.
+// MEASURED (round 2, B200, batch 64, same box): correct (every parity test passes with SSP_TC2_CLUSTER=4) but SLOWER -- forward
+// 4.61 -> 5.22 ms, data gradient 2.56 -> 2.70 ms, weight gradient (wgrad_tc2.cu) 3.54 -> 4.38 ms per step; 13x13 forward 240 -> 284 us
+// at 63 % instead of 77 % tensor-active.  Two reasons seen: only 33 clusters of 4 are co-resident (cudaOccupancyMaxActiveClusters:
+// 132 of the 148 SMs), and a ring slot is now released only when BOTH pairs have consumed it while a pair can start a k-block only
+// when all four producers have delivered -- the pairs run in lockstep and every hiccup of one stalls the other.  Default stays
+// CSZ = 2; SSP_TC2_CLUSTER=4 keeps the path reachable for the next attempt (2 x 2 clusters of 8 with both operands shared).
+template <int MODE, int CSZ>
+__global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(CSZ, 1, 1) conv_tc2_kernel(const __grid_constant__ ConvTc2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16-B aligned: round up to 1024 (swizzle-128B atoms)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -116,9 +135,13 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;      // work items; m_tiles counts 256-row pair tiles
-  const uint32_t rank = cluster_ctarank();
-  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  constexpr int NP = CSZ / 2;                                     // CTA pairs per cluster
+  const int total_tiles = ((p.m_tiles + NP - 1) / NP) * p.n_tiles * p.ksplit;      // work items of a CLUSTER; m_tiles counts 256-row pair tiles
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1;                                // rank inside the CTA pair (0 = leader: issues the MMAs, owns full / tempty)
+  const uint32_t pr = crank >> 1;                                 // pair inside the cluster
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * pr)), all_mask = (uint16_t)((1u << CSZ) - 1);
+  const int cid = blockIdx.x / CSZ, ncl = gridDim.x / CSZ;
   const int kblocks = p.taps * p.kc_per_tap;
 
   if (warp == 0 && lane == 0) {
@@ -127,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
     if (p.n_terms == 3) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmB[1]); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NP); }    // a slot is free when EVERY pair that reads what lands in it has consumed it
     for (int b = 0; b < 2; b++) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }
     fence_barrier_init();
   }
@@ -147,9 +170,11 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
       const uint32_t tx = 2u * (uint32_t)(p.n_terms == 3 ? 2 : 1) * (uint32_t)(kABytes + p.b_bytes);   // both CTAs' bytes
       for (int w = cid; w < total_tiles; w += ncl) {
         const int t = w / p.ksplit, ks = w - t * p.ksplit;
-        const int mt = t / p.n_tiles, nt = t % p.n_tiles;
+        const int mt = (t / p.n_tiles) * NP + (int)pr, nt = t % p.n_tiles;
         const int m0 = mt * 256 + (int)rank * 128, n0 = nt * p.bn + (int)rank * (p.bn / 2);
         const int kb0 = ks * kblocks / p.ksplit, kb1 = (ks + 1) * kblocks / p.ksplit;
+        const int nq = n0 + (int)pr * (p.bn / 4), qoff = (int)pr * (p.b_bytes / 2);      // CSZ == 4: this CTA's quarter of the weight tile
+        const uint16_t bmask = (uint16_t)((1u << rank) | (1u << (rank + 2)));             // ... goes to the same half of both pairs
         {
           for (int kb = kb0; kb < kb1; kb++) {
             const int tap = kb / p.kc_per_tap, kc = kb - tap * p.kc_per_tap;
@@ -161,10 +186,16 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
             tma_load_2d_pair(sa, &p.tmA[0], &full_bar[stage], kc * 64, arow);
             if (p.n_terms == 3) {
               tma_load_2d_pair(sa + kABytes, &p.tmA[1], &full_bar[stage], kc * 64, arow);
-              tma_load_2d_pair(sa + 2 * kABytes, &p.tmB[0], &full_bar[stage], kcol_b, n0);
-              tma_load_2d_pair(sa + 2 * kABytes + p.b_bytes, &p.tmB[1], &full_bar[stage], kcol_b, n0);
+              if (CSZ == 2) {
+                tma_load_2d_pair(sa + 2 * kABytes, &p.tmB[0], &full_bar[stage], kcol_b, n0);
+                tma_load_2d_pair(sa + 2 * kABytes + p.b_bytes, &p.tmB[1], &full_bar[stage], kcol_b, n0);
+              } else {
+                tma_load_2d_pair_mc(sa + 2 * kABytes + qoff, &p.tmB[0], &full_bar[stage], kcol_b, nq, bmask);
+                tma_load_2d_pair_mc(sa + 2 * kABytes + p.b_bytes + qoff, &p.tmB[1], &full_bar[stage], kcol_b, nq, bmask);
+              }
             } else {
-              tma_load_2d_pair(sa + kABytes, &p.tmB[0], &full_bar[stage], kcol_b, n0);
+              if (CSZ == 2) tma_load_2d_pair(sa + kABytes, &p.tmB[0], &full_bar[stage], kcol_b, n0);
+              else tma_load_2d_pair_mc(sa + kABytes + qoff, &p.tmB[0], &full_bar[stage], kcol_b, nq, bmask);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -203,10 +234,10 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
             }
             umma_f16_pair(d_tmem, dah, dbh, p.idesc, acc);  acc = 1;
           }
-          umma_commit_pair(&empty_bar[stage]);            // smem slot free (in both CTAs) once these MMAs retire
+          umma_commit_pair(&empty_bar[stage], all_mask);  // this pair is done with the slot (every producer of the cluster hears it)
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&tfull_bar[buf]);                // accumulator complete -> both epilogues
+        umma_commit_pair(&tfull_bar[buf], pair_mask);     // accumulator complete -> both epilogues of this pair
       }
     }
   } else if (warp >= 4) {
@@ -216,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
     for (int w = cid; w < total_tiles; w += ncl, it++) {
       const int buf = it & 1;
       const int t = w / p.ksplit;
-      const int mt = t / p.n_tiles, nt = t % p.n_tiles;
+      const int mt = (t / p.n_tiles) * NP + (int)pr, nt = t % p.n_tiles;
       const long long m = (long long)mt * 256 + rank * 128 + q * 32 + lane;
       const int n0 = nt * p.bn;
       bool valid = false;
@@ -312,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(2, 1, 1) conv_tc
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tempty_bar[buf]);
+      if (lane == 0) mbar_arrive_rank(&tempty_bar[buf], 2 * pr);
     }
     if (p.epi == EPI_STATS) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -382,17 +413,23 @@ int conv_gemm_tc2(const void* a_hi, const void* a_lo, long long a_rows, int a_ld
   if (fa) p.fa = *fa; else p.fa = FusedAct{nullptr, nullptr, 1.f, nullptr, nullptr, 0, 0};
   int rc = 0;
   rc |= tmap_2d_16bit(&p.tmA[0], a_hi, (uint64_t)cin, (uint64_t)a_rows, (uint64_t)a_ld, 64, 128, a_fmt == FMT_BF16);
-  rc |= tmap_2d_16bit(&p.tmB[0], b_hi, (uint64_t)taps * cin, (uint64_t)b_rows, (uint64_t)b_ld, 64, bn / 2, b_fmt == FMT_BF16);
+  // clusters of two pairs (weight tile multicast) unless switched off, a one-tile layer, or split K (its work items are not paired)
+  static const int csz_env = []() { const char* e = getenv("SSP_TC2_CLUSTER"); return e ? atoi(e) : 2; }();      // 4 = opt-in (measured slower, see the kernel comment)
+  const int csz = (csz_env == 4 && p.m_tiles >= 2) ? 4 : 2;
+  const int brows = csz == 4 ? bn / 4 : bn / 2;
+  rc |= tmap_2d_16bit(&p.tmB[0], b_hi, (uint64_t)taps * cin, (uint64_t)b_rows, (uint64_t)b_ld, 64, brows, b_fmt == FMT_BF16);
   if (p.n_terms == 3) {
     rc |= tmap_2d_16bit(&p.tmA[1], a_lo, (uint64_t)cin, (uint64_t)a_rows, (uint64_t)a_ld, 64, 128, a_fmt == FMT_BF16);
-    rc |= tmap_2d_16bit(&p.tmB[1], b_lo, (uint64_t)taps * cin, (uint64_t)b_rows, (uint64_t)b_ld, 64, bn / 2, b_fmt == FMT_BF16);
+    rc |= tmap_2d_16bit(&p.tmB[1], b_lo, (uint64_t)taps * cin, (uint64_t)b_rows, (uint64_t)b_ld, 64, brows, b_fmt == FMT_BF16);
   }
   if (rc) return fail_msg(SSP_ERR_DRIVER, "conv_gemm_tc2: cuTensorMapEncodeTiled failed (no driver, or misaligned operand)");
   const int smem_bytes = stages * p.stage_bytes + fixed;
   static int configured = 0;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, __FILE__, __LINE__);
     configured = 1;
   }
@@ -401,7 +438,7 @@ int conv_gemm_tc2(const void* a_hi, const void* a_lo, long long a_rows, int a_ld
   // the partial sums are added with fp32 vector atomics into the zeroed output.  (49 x 3 = 147 ~ 2 x 74: three cuts fit almost exactly.)
   p.ksplit = 1;
   static const int splitk_on = []() { const char* e = getenv("SSP_DGRAD_SPLITK"); return e ? atoi(e) : 0; }();
-  if (splitk_on && epi == EPI_F32 && !fa && out) {
+  if (splitk_on && csz == 2 && epi == EPI_F32 && !fa && out) {
     const int npairs = g_num_sms2 / 2, tiles = p.m_tiles * p.n_tiles, kb = taps * p.kc_per_tap;
     double best = (double)tiles / ((double)((tiles + npairs - 1) / npairs) * npairs);
     for (int sp = 2; sp <= 4; sp++) {
@@ -415,10 +452,34 @@ int conv_gemm_tc2(const void* a_hi, const void* a_lo, long long a_rows, int a_ld
       if (e != cudaSuccess) return fail_cuda(e, __FILE__, __LINE__);
     }
   }
-  const int total = p.m_tiles * p.n_tiles * p.ksplit;
-  int pairs = g_num_sms2 / 2; if (total < pairs) pairs = total;
-  if (fa) conv_tc2_kernel<1><<<2 * pairs, kThreads, smem_bytes, stream>>>(p);
-  else conv_tc2_kernel<0><<<2 * pairs, kThreads, smem_bytes, stream>>>(p);     // __cluster_dims__(2,1,1): CTA pairs on one TPC
+  const int np = csz / 2;
+  const int total = ((p.m_tiles + np - 1) / np) * p.n_tiles * p.ksplit;      // work items of a cluster
+  // A persistent kernel must not launch more clusters than are co-resident: a cluster of 4 needs 4 free SMs in ONE GPC, and the
+  // GPCs of a B200 do not all hold a multiple of 4 (round 2: with 148 / 4 = 37 clusters the stragglers ran as a second wave after
+  // the first had finished ALL the work items of their stride -- forward 4.8 -> 6.7 ms).  Ask the driver once per kernel.
+  static int max_clusters4[2] = {0, 0};
+  int clusters = g_num_sms2 / csz;
+  if (csz == 4) {
+    int& mc = max_clusters4[fa ? 1 : 0];
+    if (!mc) {
+      cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(4 * (g_num_sms2 / 4)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 227 * 1024;
+      cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      cudaError_t e = fa ? cudaOccupancyMaxActiveClusters(&n, conv_tc2_kernel<1, 4>, &cfg) : cudaOccupancyMaxActiveClusters(&n, conv_tc2_kernel<0, 4>, &cfg);
+      mc = (e == cudaSuccess && n > 0) ? n : g_num_sms2 / 8;                // conservative if the query is not available
+    }
+    if (clusters > mc) clusters = mc;
+  }
+  if (total < clusters) clusters = total;
+  const unsigned grid = (unsigned)(csz * clusters);
+  if (csz == 4) {
+    if (fa) conv_tc2_kernel<1, 4><<<grid, kThreads, smem_bytes, stream>>>(p);
+    else conv_tc2_kernel<0, 4><<<grid, kThreads, smem_bytes, stream>>>(p);
+  } else {
+    if (fa) conv_tc2_kernel<1, 2><<<grid, kThreads, smem_bytes, stream>>>(p);
+    else conv_tc2_kernel<0, 2><<<grid, kThreads, smem_bytes, stream>>>(p);   // __cluster_dims__(2,1,1): CTA pairs on one TPC
+  }
   SSP_CHECK_LAUNCH();
   return SSP_OK;
 }

@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(256, MINB) l0_fused_fwd_kernel(const float* __
 // ------------------------------------------------------------------------------------------------ backward over the pooled gradient
 // t1[k][c] (k < 27) += sum_windows dz * patch(argmax)[k],  t1[27][c] += sum dz      (fp64 accumulators, zeroed by the launcher)
 // lane = channel; a warp walks the 16 windows of one window row of the tile.
-__global__ void __launch_bounds__(256, 2) l0_bwd_kernel(const float* __restrict__ x, const void* __restrict__ g, int g_f16, int g_ld, int g_c0,
+template <bool G16>      // the pooled gradient plane holds fp16 (SSP_EPI_F16) or fp32 -- compile-time, so that the 16 loads of a window row stay batched
+__global__ void __launch_bounds__(256, 2) l0_bwd_kernel(const float* __restrict__ x, const void* __restrict__ g, int g_ld, int g_c0,
                                                         const uint8_t* __restrict__ code, float slope, int N, int H, int W,
                                                         double* __restrict__ t1) {
   __shared__ float sin[3][kTH + 2][kInW];
@@ -271,7 +272,8 @@ __global__ void __launch_bounds__(256, 2) l0_bwd_kernel(const float* __restrict_
       const bool ok = row_ok && (2 * ws + 1 < W);
       const long long row = ok ? gh.row(t.n, hs, ws) : 0;
       const long long ge = row * g_ld + g_c0 + lane;
-      gv[wc] = !ok ? 0.f : (g_f16 ? __half2float(__ldg(reinterpret_cast<const __half*>(g) + ge)) : __ldg(reinterpret_cast<const float*>(g) + ge));   // out-of-image windows: dz = 0
+      if (G16) gv[wc] = ok ? __half2float(__ldg(reinterpret_cast<const __half*>(g) + ge)) : 0.f;      // out-of-image windows: dz = 0
+      else gv[wc] = ok ? __ldg(reinterpret_cast<const float*>(g) + ge) : 0.f;
       cd[wc] = ok ? (int)__ldg(code + row * kC0 + lane) : 0;
     }
     __syncthreads();
@@ -371,7 +373,8 @@ int l0_bwd(const float* x, const void* g, int g_f16, int g_ld, int g_c0, const u
   if (nt <= 0 || nt > 0x7fffffffLL) return fail_msg(SSP_ERR_ARG, "l0_bwd: bad shape");
   cudaError_t e = cudaMemsetAsync(t1, 0, sizeof(double) * kG * kC0, s);
   if (e != cudaSuccess) return fail_cuda(e, __FILE__, __LINE__);
-  l0_bwd_kernel<<<l0_grid(nt, 2), 256, 0, s>>>(x, g, g_f16, g_ld, g_c0, code, slope, N, H, W, t1);
+  if (g_f16) l0_bwd_kernel<true><<<l0_grid(nt, 2), 256, 0, s>>>(x, g, g_ld, g_c0, code, slope, N, H, W, t1);
+  else l0_bwd_kernel<false><<<l0_grid(nt, 2), 256, 0, s>>>(x, g, g_ld, g_c0, code, slope, N, H, W, t1);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
 

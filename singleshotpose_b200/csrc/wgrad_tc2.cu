@@ -1,5 +1,4 @@
-// EXPERIMENTAL (opt-in: SSP_WGRAD_IMPL=tc2; NOT yet run on hardware -- written at the end of round 1 after the GPU budget was
-// spent; the default path is wgrad_tc.cu).  CTA-pair version of the weight-gradient GEMM:
+// CTA-pair version of the weight-gradient GEMM (default for layers with cout, cin multiples of 256; round 2: 4.0 -> 3.5 ms/step):
 //     dW[co, tap, ci] += sum_m dY[m, co] * X[m + shift(tap), ci]
 // Why: wgrad_tc.cu is bound by the L2->SMEM fill rate, not by the tensor pipe (profiles/r01_experiments.md: 43 % tensor).
 // Per 64-row k-block a 1-CTA item stages dY 128 ch (16 KB) + X 256 ch (32 KB) = 48 KB for 128x256x64 MACs = 87 FLOP/B.
@@ -9,8 +8,12 @@
 // One tap per work item, double-buffered 2 x 256-column accumulators; pair mechanics (leader-credited TMA, multicast commits,
 // remote tempty arrives) are those of conv_tc2.cu.  Eligible layers: cout % 256 == 0 and cin % 256 == 0 (all 13x13 and 26x26
 // 3x3 / 1x1 layers of yolo-pose.cfg); anything else returns 1 and the caller falls back to wgrad_tc.cu.
+// Clusters of TWO pairs (CSZ = 4, cout % 512 == 0): the pairs take neighbouring 256-channel blocks of dY and the SAME X tile, every CTA
+// fetches one of its two X boxes and multicasts it to its counterpart in the other pair -- 24 KB instead of 32 KB requested from
+// L2 per CTA and k-block (the fill rate is bounded by what a CTA requests, tools/probes/mc_probe2.cu; see conv_tc2.cu).
 #include "ssp_common.cuh"
 #include "tmap.cuh"
+#include <stdlib.h>
 
 namespace ssp {
 
@@ -53,13 +56,19 @@ __device__ __forceinline__ void w2_umma_pair(uint32_t tmem_d, uint64_t desc_a, u
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void w2_commit_pair(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+__device__ __forceinline__ void w2_tma_pair_mc(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
 }
-__device__ __forceinline__ void w2_arrive_leader(uint64_t* bar) {
-  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
-               ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void w2_commit_pair(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void w2_arrive_rank(uint64_t* bar, uint32_t target) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+               ::"r"(smem_u32(bar)), "r"(target) : "memory");
 }
 __device__ __forceinline__ void w2_tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
@@ -70,7 +79,8 @@ __device__ __forceinline__ void w2_tmem_dealloc(uint32_t taddr, uint32_t ncols) 
 }
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads2, 1) __cluster_dims__(2, 1, 1) wgrad_tc2_kernel(const __grid_constant__ WgradTc2Params p) {
+template <int CSZ>
+__global__ void __launch_bounds__(kThreads2, 1) __cluster_dims__(CSZ, 1, 1) wgrad_tc2_kernel(const __grid_constant__ WgradTc2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * kStage2);
@@ -80,14 +90,17 @@ __global__ void __launch_bounds__(kThreads2, 1) __cluster_dims__(2, 1, 1) wgrad_
   uint32_t* tmem_ptr = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = w2_ctarank();
-  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
-  const int items = p.co_pairs * p.ci_tiles * p.taps * p.splits;
+  constexpr int NP = CSZ / 2;                                     // CTA pairs per cluster
+  const uint32_t crank = w2_ctarank();
+  const uint32_t rank = crank & 1, pr = crank >> 1;               // rank inside the pair (0 = leader), pair inside the cluster
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * pr)), all_mask = (uint16_t)((1u << CSZ) - 1);
+  const int cid = blockIdx.x / CSZ, ncl = gridDim.x / CSZ;
+  const int items = (p.co_pairs / NP) * p.ci_tiles * p.taps * p.splits;      // work items of a cluster
   const int kb_per_split = (p.kblocks_total + p.splits - 1) / p.splits;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmDy); tma_prefetch_desc(&p.tmX); }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NP); }   // free when every pair reading the slot is done
     for (int b = 0; b < 2; b++) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }   // 4 epilogue warps x 2 CTAs
     fence_barrier_init();
   }
@@ -100,7 +113,7 @@ __global__ void __launch_bounds__(kThreads2, 1) __cluster_dims__(2, 1, 1) wgrad_
 
   // item -> (split, tap, ci tile, co pair); co fastest so that concurrently running pairs share X tiles in L2
   auto decode = [&](int it, int& co_p, int& ci_t, int& tap, int& kb0, int& kb1) {
-    co_p = it % p.co_pairs; it /= p.co_pairs;
+    co_p = (it % (p.co_pairs / NP)) * NP + (int)pr; it /= (p.co_pairs / NP);
     ci_t = it % p.ci_tiles; it /= p.ci_tiles;
     tap = it % p.taps; it /= p.taps;
     kb0 = it * kb_per_split;
@@ -121,8 +134,13 @@ __global__ void __launch_bounds__(kThreads2, 1) __cluster_dims__(2, 1, 1) wgrad_
           const int row = kb * 64;
           w2_tma_pair(s, &p.tmDy, &full_bar[stage], co0, row);
           w2_tma_pair(s + kBox2, &p.tmDy, &full_bar[stage], co0 + 64, row);
-          w2_tma_pair(s + 2 * kBox2, &p.tmX, &full_bar[stage], ci0, row + p.shifts[tap]);
-          w2_tma_pair(s + 3 * kBox2, &p.tmX, &full_bar[stage], ci0 + 64, row + p.shifts[tap]);
+          if (CSZ == 2) {
+            w2_tma_pair(s + 2 * kBox2, &p.tmX, &full_bar[stage], ci0, row + p.shifts[tap]);
+            w2_tma_pair(s + 3 * kBox2, &p.tmX, &full_bar[stage], ci0 + 64, row + p.shifts[tap]);
+          } else {     // one of this CTA's two X boxes, delivered to the same half of both pairs
+            w2_tma_pair_mc(s + (2 + (int)pr) * kBox2, &p.tmX, &full_bar[stage], ci0 + (int)pr * 64, row + p.shifts[tap],
+                           (uint16_t)((1u << rank) | (1u << (rank + 2))));
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -148,10 +166,10 @@ __global__ void __launch_bounds__(kThreads2, 1) __cluster_dims__(2, 1, 1) wgrad_
             w2_umma_pair(d_tmem, da, db, p.idesc, (k == 0) ? acc : 1u);
           }
           acc = 1;
-          w2_commit_pair(&empty_bar[stage]);      // slot free in BOTH CTAs once these MMAs retire
+          w2_commit_pair(&empty_bar[stage], all_mask);      // this pair is done with the slot (every producer of the cluster hears it)
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        w2_commit_pair(&tfull_bar[buf]);          // accumulator complete -> both epilogues
+        w2_commit_pair(&tfull_bar[buf], pair_mask);       // accumulator complete -> both epilogues of this pair
       }
     }
   } else if (warp >= 4) {
@@ -178,7 +196,7 @@ __global__ void __launch_bounds__(kThreads2, 1) __cluster_dims__(2, 1, 1) wgrad_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) w2_arrive_leader(&tempty_bar[buf]);
+      if (lane == 0) w2_arrive_rank(&tempty_bar[buf], 2 * pr);
     }
   }
   tc_fence_before();
@@ -209,8 +227,23 @@ int wgrad_gemm_tc2(const void* dy, long long dy_rows, int dy_ld, int cout, int d
   p.taps = taps;
   for (int t = 0; t < 9; t++) p.shifts[t] = (taps == 9) ? ((t / 3) - 1) * g.Wp() + ((t % 3) - 1) : 0;
   p.cout = cout; p.cin = cin;
-  const int pairs = g_num_sms_w2 / 2;
-  const int base_items = p.co_pairs * p.ci_tiles * taps;
+  static const int csz_env = []() { const char* e = getenv("SSP_TC2_CLUSTER"); return e ? atoi(e) : 2; }();      // 4 = opt-in (measured slower, see the kernel comment)
+  const int csz = (csz_env == 4 && (p.co_pairs % 2) == 0) ? 4 : 2;
+  int pairs = g_num_sms_w2 / csz;                                         // clusters that fit the chip ...
+  if (csz == 4) {                                                         // ... and are co-resident (see conv_tc2.cu: GPCs are not multiples of 4 SMs)
+    static int mc = 0;
+    if (!mc) {
+      cudaFuncSetAttribute(wgrad_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(4 * (g_num_sms_w2 / 4)); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = 227 * 1024;
+      cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, wgrad_tc2_kernel<4>, &cfg);
+      mc = (e == cudaSuccess && n > 0) ? n : g_num_sms_w2 / 8;
+    }
+    if (pairs > mc) pairs = mc;
+  }
+  const int base_items = (p.co_pairs / (csz / 2)) * p.ci_tiles * taps;    // work items of a cluster
   // split K only when one pass leaves most pairs idle or the last wave mostly empty; keep >= 32 k-blocks per item
   int max_splits = p.kblocks_total / 32; if (max_splits < 1) max_splits = 1;
   int best = 1; double best_eff = 0.0;
@@ -233,13 +266,15 @@ int wgrad_gemm_tc2(const void* dy, long long dy_rows, int dy_ld, int cout, int d
   if (rc) return fail_msg(SSP_ERR_DRIVER, "wgrad_gemm_tc2: cuTensorMapEncodeTiled failed");
   static int configured = 0;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, __FILE__, __LINE__);
     configured = 1;
   }
   const int items = base_items * p.splits;
   int use = items < pairs ? items : pairs;
-  wgrad_tc2_kernel<<<2 * use, kThreads2, stages * kStage2 + fixed, stream>>>(p);     // __cluster_dims__(2,1,1): CTA pairs on one TPC
+  if (csz == 4) wgrad_tc2_kernel<4><<<4 * use, kThreads2, stages * kStage2 + fixed, stream>>>(p);
+  else wgrad_tc2_kernel<2><<<2 * use, kThreads2, stages * kStage2 + fixed, stream>>>(p);     // __cluster_dims__(2,1,1): CTA pairs on one TPC
   SSP_CHECK_LAUNCH();
   return SSP_OK;
 }

@@ -8,7 +8,7 @@ rows = list(csv.reader(io.StringIO(raw)))
 print(rows[0][1] if rows and len(rows[0]) > 1 else "?")
 hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-body = [r for r in rows[2:] if len(r) == len(hdr)]
+body = [r for r in rows[2:] if len(r) == len(hdr) and r[ix["# Samples"]].replace(",", "").isdigit()]      # a second (CUDA-C) view repeats the header
 tot = sum(int(r[ix["# Samples"]] or 0) for r in body)
 print("total samples", tot, " instructions", len(body))
 order = sorted(range(len(body)), key=lambda k: -int(body[k][ix["# Samples"]] or 0))[:top]
