@@ -334,7 +334,7 @@ def main():
         except Exception:
             traffic, traffic_detail = None, None
     roofline = {"bound": "tensor", "kernel": "conv GEMM launches of the forward and data-gradient passes: conv_tc2_kernel<0> (CTA pairs, N tile >= 128), "
-                                             "conv_band_kernel (3x3, N < 128), conv_tc_kernel (1x1, N < 128)", "achieved": achieved, "peak": pk["tflops"],
+                                             "conv_bandt_kernel (operand-swapped, N <= 64 split-fp16 / <= 128 single-term), conv_tc_kernel (the 20-channel head)", "achieved": achieved, "peak": pk["tflops"],
                 "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": pk["src"],
                 "executed_tflops": executed, "frac_executed": executed / pk["tflops"],
                 "launches_per_step": conv_n // max(args.steps, 1), "share_of_step": conv_t / (ms_eager * 1e-3) if ms_eager else None,
@@ -343,7 +343,7 @@ def main():
                                "every GEMM launch" % (args.steps, ms_eager / args.steps, ms / args.steps),
                 "eager_ms_per_step": ms_eager / args.steps, "graph_ms_per_step": ms / args.steps,
                 "note": "achieved/frac count ALGORITHMIC FLOPs; the forward launches execute 3 MMAs per algorithmic MAC (split-fp16 operands are "
-                        "what meets the 1e-3 logits tolerance, DESIGN.md section 2), executed_tflops counts those; layer 0 runs in conv0_direct_kernel "
+                        "what meets the 1e-3 logits tolerance, DESIGN.md section 2), executed_tflops counts those; blocks 0-1 run in the CUDA-core l0_fused kernels (csrc/l0_fused.cu) "
                         "(HBM-bound, not part of this kernel)",
                 "per_kind": per_kind,
                 "step_tflops_algorithmic": STEP_GFLOP_PER_IMG * 1e9 * B / (ms / args.steps * 1e-3) / 1e12}
@@ -367,6 +367,23 @@ def main():
         e0.record(); utils.pnp_batched(P3, uv, K); e1.record(); torch.cuda.synchronize()
         tg = e0.elapsed_time(e1) * 1e-3
         pnp = {"poses_per_s": n / tg, "n": n, "points": 9, "sigma_px": 0.5, "ms": tg * 1e3}
+        # achieved fp64 FLOP/s from the kernel's own work counters on a 64k sample: flop model of pnp_core.h per problem =
+        #   4.7e3 (block assembly, one factorisation, 6 inverse iterations, the positive-definiteness proof)
+        # + 1.0e3 per Rayleigh-quotient step + 1.6e4 per sweep of the 12x12 Jacobi fall-back
+        # + 3.1e3 per accepted LM iteration (Jacobian, J^T J) + 5.5e2 per LM linear solve (6x6 Cholesky + reprojection error)
+        from singleshotpose_b200._lib import call as _call, ptr as _ptr, stream_ptr as _sp
+        ns = 65536
+        Rw = torch.empty(ns, 9, dtype=torch.float64, device=dev); tw = torch.empty(ns, 3, dtype=torch.float64, device=dev)
+        work = torch.zeros(ns, 3, dtype=torch.int32, device=dev)
+        _call("ssp_pnp_batched_work", _ptr(P3), 1, _ptr(uv), _ptr(K), 9, ns, 20, _ptr(Rw), _ptr(tw), _ptr(work), _sp())
+        w = work.cpu().numpy().astype("float64")
+        rq = (-w[:, 0]).clip(min=0); sweeps = w[:, 0].clip(min=0)
+        flop = 4.7e3 + 1.0e3 * rq + 1.6e4 * sweeps + 3.1e3 * w[:, 1] + 5.5e2 * w[:, 2]
+        pnp["flop_per_problem_model"] = float(flop.mean())
+        pnp["fp64_gflops"] = float(flop.mean()) * n / tg / 1e9
+        pnp["work_mean"] = {"rq_steps": float(rq.mean()), "jacobi_fallback_fraction": float((sweeps > 0).mean()),
+                            "lm_iterations": float(w[:, 1].mean()), "lm_solves": float(w[:, 2].mean())}
+        pnp["bound"] = "fp64 ALU / dependent-issue latency (one problem per thread, 120 B of HBM traffic per problem)"
         try:
             import cv2
             m = 2000

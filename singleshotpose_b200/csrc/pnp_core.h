@@ -148,6 +148,151 @@ SSP_HD int jacobi_eig(double A[n][n], double V[n][n]) {
 #endif
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Smallest eigenpair of the DLT normal matrix WITHOUT touching the 12 x 12 matrix: it is a 3 x 3 arrangement of 4 x 4 blocks,
+//     M = [[S, 0, -Sx], [0, S, -Sy], [-Sx, -Sy, Sq]],     S = sum XX^T, Sx = sum x XX^T, Sy = sum y XX^T, Sq = sum (x^2 + y^2) XX^T,
+// so (M - mu I) y = b is solved by eliminating the first two block rows (A = S - mu I is SPD, A^-1 from a 4 x 4 Cholesky):
+//     C(mu) y3 = b3 + Sx A^-1 b1 + Sy A^-1 b2,   C(mu) = (Sq - mu I) - Sx A^-1 Sx - Sy A^-1 Sy,   y1 = A^-1 (b1 + Sx y3),  y2 likewise.
+// Three inverse iterations at mu ~ 0 (M is PSD) pull the iterate towards the smallest eigenvector, Rayleigh-quotient iteration
+// (mu = v^T M v, cubic convergence) finishes it to machine precision, and a last block-Cholesky of M - (rho - eps) I PROVES that no
+// eigenvalue lies below the one found (Sylvester: A and C(mu) positive definite <=> M - mu I positive definite).  If any step fails --
+// a Cholesky that should succeed does not, no convergence, the proof fails -- the caller falls back to the cyclic Jacobi on the full
+// 12 x 12 matrix, so the result is the same eigenvector either way (up to sign, fixed by det > 0 below).  Everything lives in
+// registers (4 x 4 blocks, static indices): ~4e3 flop instead of ~1e5 flop of local-memory Jacobi -- the single-image latency of
+// valid.py's pnp() call is what this is for (round 2: batch-1 inference 2.1 ms with the Jacobi, of which 0.6 ms in this solve).
+SSP_HD bool chol4_inv(const double A[4][4], double Ai[4][4]) {       // SPD inverse; false if a pivot is not positive
+  double L[4][4];
+  for (int j = 0; j < 4; j++) {
+    double d = A[j][j];
+    for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
+    if (!(d > 0.0)) return false;
+    L[j][j] = sqrt(d);
+    for (int i = j + 1; i < 4; i++) {
+      double v = A[i][j];
+      for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k];
+      L[i][j] = v / L[j][j];
+    }
+  }
+  for (int c = 0; c < 4; c++) {                                       // solve L L^T x = e_c
+    double y[4];
+    for (int i = 0; i < 4; i++) { double v = (i == c) ? 1.0 : 0.0; for (int k = 0; k < i; k++) v -= L[i][k] * y[k]; y[i] = v / L[i][i]; }
+    for (int i = 3; i >= 0; i--) { double v = y[i]; for (int k = i + 1; k < 4; k++) v -= L[k][i] * Ai[k][c]; Ai[i][c] = v / L[i][i]; }
+  }
+  return true;
+}
+SSP_HD bool gauss4_solve(const double A[4][4], const double b[4], double x[4]) {     // general 4 x 4, partial pivoting (C(mu) is indefinite / nearly singular in the RQI steps)
+  double a[4][5];
+  for (int i = 0; i < 4; i++) { for (int j = 0; j < 4; j++) a[i][j] = A[i][j]; a[i][4] = b[i]; }
+  for (int c = 0; c < 4; c++) {
+    int piv = c; double best = fabs(a[c][c]);
+    for (int r = c + 1; r < 4; r++) if (fabs(a[r][c]) > best) { best = fabs(a[r][c]); piv = r; }
+    if (best == 0.0) return false;
+    for (int j = 0; j < 5; j++) {                                     // row swap through selects: no dynamic register indexing
+      double top = a[c][j], oth = top;
+      for (int r = c + 1; r < 4; r++) if (r == piv) oth = a[r][j];
+      for (int r = c + 1; r < 4; r++) if (r == piv) a[r][j] = top;
+      a[c][j] = oth;
+    }
+    const double inv = 1.0 / a[c][c];
+    for (int r = c + 1; r < 4; r++) {
+      const double f = a[r][c] * inv;
+      for (int j = c; j < 5; j++) a[r][j] -= f * a[c][j];
+    }
+  }
+  for (int i = 3; i >= 0; i--) { double v = a[i][4]; for (int k = i + 1; k < 4; k++) v -= a[i][k] * x[k]; x[i] = v / a[i][i]; }
+  return true;
+}
+SSP_HD void mat4_vec(const double A[4][4], const double v[4], double o[4]) {
+  for (int i = 0; i < 4; i++) o[i] = A[i][0] * v[0] + A[i][1] * v[1] + A[i][2] * v[2] + A[i][3] * v[3];
+}
+struct DltBlocks { double S[4][4], Sx[4][4], Sy[4][4], Sq[4][4]; };
+// A^-1 and C(mu); false if S - mu I is not positive definite
+SSP_HD bool dlt_factor(const DltBlocks& B, double mu, double Ai[4][4], double C[4][4]) {
+  double A[4][4];
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) A[i][j] = B.S[i][j] - (i == j ? mu : 0.0);
+  if (!chol4_inv(A, Ai)) return false;
+  double Tx[4][4], Ty[4][4];
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < 4; k++) { a += Ai[i][k] * B.Sx[k][j]; b += Ai[i][k] * B.Sy[k][j]; }
+    Tx[i][j] = a; Ty[i][j] = b;
+  }
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) {
+    double v = B.Sq[i][j] - (i == j ? mu : 0.0);
+    for (int k = 0; k < 4; k++) v -= B.Sx[i][k] * Tx[k][j] + B.Sy[i][k] * Ty[k][j];
+    C[i][j] = v;
+  }
+  return true;
+}
+SSP_HD bool dlt_solve(const DltBlocks& B, const double Ai[4][4], const double C[4][4], const double b[12], double y[12]) {
+  double t1[4], t2[4], u[4], rhs[4];
+  mat4_vec(Ai, b, t1); mat4_vec(Ai, b + 4, t2);
+  mat4_vec(B.Sx, t1, u); for (int i = 0; i < 4; i++) rhs[i] = b[8 + i] + u[i];
+  mat4_vec(B.Sy, t2, u); for (int i = 0; i < 4; i++) rhs[i] += u[i];
+  if (!gauss4_solve(C, rhs, y + 8)) return false;
+  mat4_vec(B.Sx, y + 8, u); for (int i = 0; i < 4; i++) u[i] += b[i];
+  mat4_vec(Ai, u, y);
+  mat4_vec(B.Sy, y + 8, u); for (int i = 0; i < 4; i++) u[i] += b[4 + i];
+  mat4_vec(Ai, u, y + 4);
+  return true;
+}
+SSP_HD void dlt_matvec(const DltBlocks& B, const double v[12], double o[12]) {
+  double a[4], b[4];
+  mat4_vec(B.S, v, a); mat4_vec(B.Sx, v + 8, b); for (int i = 0; i < 4; i++) o[i] = a[i] - b[i];
+  mat4_vec(B.S, v + 4, a); mat4_vec(B.Sy, v + 8, b); for (int i = 0; i < 4; i++) o[4 + i] = a[i] - b[i];
+  mat4_vec(B.Sq, v + 8, o + 8); mat4_vec(B.Sx, v, a); mat4_vec(B.Sy, v + 4, b); for (int i = 0; i < 4; i++) o[8 + i] -= a[i] + b[i];
+}
+SSP_HD bool normalize12(double v[12]) {
+  double n = 0.0; for (int i = 0; i < 12; i++) n += v[i] * v[i];
+  if (!(n > 0.0) || !(n < 1e300)) return false;
+  n = 1.0 / sqrt(n); for (int i = 0; i < 12; i++) v[i] *= n;
+  return true;
+}
+// v (unit norm) and lambda of the smallest eigenvalue of M; false => use the Jacobi on the full matrix.
+// An attempt = 6 inverse iterations at mu ~ 0 (one factorisation), Rayleigh-quotient iteration to convergence, the proof.  When the
+// proof fails the pair found is a HIGHER eigenpair (the start vector had too little of the smallest one: ~15 % of the noisy golden
+// problems with a single attempt): it is kept, projected out of the next attempt's inverse iterations (deflation), and the next
+// attempt starts from another vector.  *steps returns the total number of Rayleigh-quotient steps.
+SSP_HD bool dlt_smallest_eigvec(const DltBlocks& B, double v[12], double* lambda, int* steps) {
+  double tr = 0.0;
+  for (int i = 0; i < 4; i++) tr += 2.0 * B.S[i][i] + B.Sq[i][i];
+  if (!(tr > 0.0)) return false;
+  double A0[4][4], C0[4][4];
+  if (!dlt_factor(B, -1e-13 * tr, A0, C0)) return false;
+  double found[2][12];                                                   // higher eigenvectors met on the way
+  int nfound = 0, total = 0;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    double Ai[4][4], C[4][4], y[12];
+    for (int i = 0; i < 12; i++) v[i] = attempt == 0 ? 1.0 + 0.0625 * i : (attempt == 1 ? ((i & 1) ? -1.0 : 1.0) * (1.0 + 0.03 * i) : ((i % 3) == 0 ? 1.5 : -0.4) + 0.01 * i);
+    normalize12(v);
+    for (int it = 0; it < 6; it++) {
+      for (int f = 0; f < nfound; f++) { double d = 0.0; for (int i = 0; i < 12; i++) d += v[i] * found[f][i]; for (int i = 0; i < 12; i++) v[i] -= d * found[f][i]; }
+      if (!dlt_solve(B, A0, C0, v, y)) return false;
+      for (int i = 0; i < 12; i++) v[i] = y[i];
+      if (!normalize12(v)) return false;
+    }
+    double rho = 0.0; bool conv = false;
+    for (int k = 0; k < 8 && !conv; k++, total++) {
+      dlt_matvec(B, v, y);
+      rho = 0.0; for (int i = 0; i < 12; i++) rho += v[i] * y[i];
+      double res = 0.0; for (int i = 0; i < 12; i++) { const double r = y[i] - rho * v[i]; res += r * r; }
+      if (sqrt(res) <= 2e-15 * tr) { conv = true; break; }
+      if (!dlt_factor(B, rho, Ai, C)) return false;
+      if (!dlt_solve(B, Ai, C, v, y)) { conv = true; break; }          // exactly singular: rho IS an eigenvalue to the last bit
+      for (int i = 0; i < 12; i++) v[i] = y[i];
+      if (!normalize12(v)) return false;
+    }
+    if (!conv) return false;
+    // proof: M - (rho - eps) I is positive definite  =>  nothing below rho - eps
+    double Ci[4][4];
+    if (dlt_factor(B, rho - 1e-10 * tr, Ai, C) && chol4_inv(C, Ci)) { *lambda = rho; *steps = total; return true; }
+    if (nfound == 2) return false;
+    for (int i = 0; i < 12; i++) found[nfound][i] = v[i];
+    nfound++;
+  }
+  return false;
+}
+
 // in-place Cholesky solve of SPD n x n system (n <= 6); returns false if not positive definite
 template <int n>
 SSP_HD bool chol_solve(double A[n][n], double b[n]) {
@@ -190,27 +335,45 @@ SSP_HD void pnp_solve_one(const float* p3, const float* q, const float* Kmat, in
   for (int i = 0; i < 2 * np; i++) m[i] = (double)q[i];
 
   // ---- DLT (cvFindExtrinsicCameraParams2, non-planar branch): smallest eigenvector of L^T L on the raw coordinates ----
-  double LL[12][12], LV[12][12];
-  for (int a = 0; a < 12; a++) for (int b = 0; b < 12; b++) LL[a][b] = 0.0;
+  // the four 4 x 4 blocks of L^T L; the smallest eigenvector through the block solve (dlt_smallest_eigvec), the cyclic Jacobi on the
+  // assembled 12 x 12 matrix only if that declines (PNP_DLT_JACOBI=1 forces it: the two must agree, tests/test_pnp_host.py)
+  DltBlocks Bk;
+  for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) { Bk.S[a][b] = 0.0; Bk.Sx[a][b] = 0.0; Bk.Sy[a][b] = 0.0; Bk.Sq[a][b] = 0.0; }
   for (int i = 0; i < np; i++) {
     const double X[4] = {M[3 * i], M[3 * i + 1], M[3 * i + 2], 1.0};
     const double x = (m[2 * i] - cx) / fx, y = (m[2 * i + 1] - cy) / fy, qq = x * x + y * y;
     for (int a = 0; a < 4; a++)
       for (int b = 0; b < 4; b++) {
         const double xx = X[a] * X[b];
-        LL[a][b] += xx; LL[4 + a][4 + b] += xx;
-        LL[a][8 + b] -= x * xx; LL[4 + a][8 + b] -= y * xx;
-        LL[8 + a][8 + b] += qq * xx;
+        Bk.S[a][b] += xx; Bk.Sx[a][b] += x * xx; Bk.Sy[a][b] += y * xx; Bk.Sq[a][b] += qq * xx;
       }
   }
-  for (int a = 0; a < 8; a++) for (int b = 8; b < 12; b++) LL[b][a] = LL[a][b];
-  const int sweeps = jacobi_eig<12>(LL, LV);
-  int kmin = 0;
-  for (int k = 1; k < 12; k++) if (LL[k][k] < LL[kmin][kmin]) kmin = k;
+  double ev[12], lam_min = 0.0; int sweeps = 0;
+#ifndef PNP_DLT_JACOBI
+#define PNP_DLT_JACOBI 0
+#endif
+  bool have = false;
+  if (!PNP_DLT_JACOBI) { int st = 0; have = dlt_smallest_eigvec(Bk, ev, &lam_min, &st); sweeps = -st; }      // work[0] < 0: block-solve steps
+  if (!have) {
+    double LL[12][12], LV[12][12];
+    for (int a = 0; a < 12; a++) for (int b = 0; b < 12; b++) LL[a][b] = 0.0;
+    for (int a = 0; a < 4; a++)
+      for (int b = 0; b < 4; b++) {
+        LL[a][b] = Bk.S[a][b]; LL[4 + a][4 + b] = Bk.S[a][b];
+        LL[a][8 + b] = -Bk.Sx[a][b]; LL[4 + a][8 + b] = -Bk.Sy[a][b];
+        LL[8 + a][8 + b] = Bk.Sq[a][b];
+      }
+    for (int a = 0; a < 8; a++) for (int b = 8; b < 12; b++) LL[b][a] = LL[a][b];
+    sweeps = jacobi_eig<12>(LL, LV);
+    int kmin = 0;
+    for (int k = 1; k < 12; k++) if (LL[k][k] < LL[kmin][kmin]) kmin = k;
+    for (int i = 0; i < 12; i++) ev[i] = LV[i][kmin];
+    lam_min = LL[kmin][kmin];
+  }
   double RR[9], tt[3];
   for (int r = 0; r < 3; r++) {
-    RR[3 * r] = LV[4 * r][kmin]; RR[3 * r + 1] = LV[4 * r + 1][kmin]; RR[3 * r + 2] = LV[4 * r + 2][kmin];
-    tt[r] = LV[4 * r + 3][kmin];
+    RR[3 * r] = ev[4 * r]; RR[3 * r + 1] = ev[4 * r + 1]; RR[3 * r + 2] = ev[4 * r + 2];
+    tt[r] = ev[4 * r + 3];
   }
   const double det = RR[0] * (RR[4] * RR[8] - RR[5] * RR[7]) - RR[1] * (RR[3] * RR[8] - RR[5] * RR[6]) + RR[2] * (RR[3] * RR[7] - RR[4] * RR[6]);
   if (det < 0) { for (int i = 0; i < 9; i++) RR[i] = -RR[i]; for (int i = 0; i < 3; i++) tt[i] = -tt[i]; }
@@ -247,7 +410,7 @@ SSP_HD void pnp_solve_one(const float* p3, const float* q, const float* Kmat, in
     }
   }
 
-  if (dbg) { dbg[0] = LL[kmin][kmin]; for (int i = 0; i < 12; i++) dbg[1 + i] = LV[i][kmin]; dbg[13] = det; for (int i = 0; i < 6; i++) dbg[14 + i] = p[i]; }
+  if (dbg) { dbg[0] = lam_min; for (int i = 0; i < 12; i++) dbg[1 + i] = ev[i]; dbg[13] = det; for (int i = 0; i < 6; i++) dbg[14 + i] = p[i]; }
 
   // ---- Levenberg-Marquardt (CvLevMarq schedule) ----
   int lam_lg10 = -3, iters = 0, solves = 0;

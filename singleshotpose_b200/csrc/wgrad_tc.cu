@@ -85,14 +85,15 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
       int stage = 0; uint32_t phase = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
         int co_t, ci_t, tap0, ntap, kb0, kb1; decode(it, co_t, ci_t, tap0, ntap, kb0, kb1);
-        const uint32_t tx = (uint32_t)(2 + ntap * nb) * kBox;
+        const bool two_dy = co_t * 128 + 64 < p.cout;
+        const uint32_t tx = (uint32_t)((two_dy ? 2 : 1) + ntap * nb) * kBox;
         for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = smem + (size_t)stage * p.stage_bytes;
           mbar_expect_tx(&full_bar[stage], tx);
           const int row = kb * 64;
           tma_load_2d(s, &p.tmDy, &full_bar[stage], co_t * 128, row);
-          tma_load_2d(s + kBox, &p.tmDy, &full_bar[stage], co_t * 128 + 64, row);
+          if (two_dy) tma_load_2d(s + kBox, &p.tmDy, &full_bar[stage], co_t * 128 + 64, row);     // else: TMEM lanes 64-127 accumulate stale smem, never read
           for (int t = 0; t < ntap; t++)
             for (int j = 0; j < nb; j++)
               tma_load_2d(s + (2 + t * nb + j) * kBox, &p.tmX, &full_bar[stage], ci_t * p.bn + j * 64, row + p.shifts[tap0 + t]);
@@ -101,19 +102,22 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0; int n = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x, n++) {
-        int co_t, ci_t, tap0, ntap, kb0, kb1; decode(it, co_t, ci_t, tap0, ntap, kb0, kb1);
-        const int buf = n % p.nbuf, use = n / p.nbuf;
-        mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
+    // MMA issuer: the whole warp runs the loops converged and ONE elected lane issues (operands then live in uniform registers;
+    // from an `if (lane == 0)` region every tcgen05.mma is wrapped in an ELECT / retry loop -- round 2, ncu: the narrow layers'
+    // weight gradients spent 70 % of the issuing warp's time in that scalar code at 20-33 % tensor-active)
+    int stage = 0; uint32_t phase = 0; int n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, n++) {
+      int co_t, ci_t, tap0, ntap, kb0, kb1; decode(it, co_t, ci_t, tap0, ntap, kb0, kb1);
+      const int buf = n % p.nbuf, use = n / p.nbuf;
+      mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.taps_per_group * p.acc_stride);
+      uint32_t acc = 0;
+      for (int kb = kb0; kb < kb1; kb++) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.taps_per_group * p.acc_stride);
-        uint32_t acc = 0;
-        for (int kb = kb0; kb < kb1; kb++) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t s = smem_u32(smem + (size_t)stage * p.stage_bytes);
+        const uint32_t s = smem_u32(smem + (size_t)stage * p.stage_bytes);
+        if (elect_one_sync()) {
           for (int t = 0; t < ntap; t += p.merge) {
             const int g = ntap - t < p.merge ? ntap - t : p.merge;                       // taps in this instruction
             const uint32_t idesc = p.idesc | ((uint32_t)((p.merge > 1 ? g * p.acc_stride : p.bn) >> 3) << 17);
@@ -124,12 +128,14 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
               umma_f16(d_tmem + (uint32_t)(t * p.acc_stride), da, db, idesc, (k == 0) ? acc : 1u);
             }
           }
-          acc = 1;
           umma_commit(&empty_bar[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[buf]);
+        acc = 1;
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (elect_one_sync()) umma_commit(&tfull_bar[buf]);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int q = warp - 4;
