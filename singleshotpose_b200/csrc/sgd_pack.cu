@@ -54,6 +54,52 @@ __global__ void __launch_bounds__(256) sgd_pack_kernel(const ssp_sgd_segment* __
   const int ci0 = cib * 64, co0 = cob * 64;
   const int lane64 = threadIdx.x & 63, grp = threadIdx.x >> 6;      // 4 groups of 64 threads
   uint16_t* f_hi = (uint16_t*)sg.f_hi; uint16_t* f_lo = (uint16_t*)sg.f_lo; uint16_t* d = (uint16_t*)sg.d;
+  if ((cin & 3) == 0 && (sg.off & 3) == 0) {
+    // vector path: thread = 4 consecutive ci of one (co, tap) row (16-B loads / stores of p, g, v; 8-B stores of the forward planes);
+    // 16 threads cover the 64 ci of a row, 16 rows per pass, 4 passes.  (Round 2: the scalar path below moved 1.3 GB in 0.45 ms =
+    // 2.9 TB/s; every access was a 4-byte load or a 2-byte store.)
+    const int q = threadIdx.x & 15, rr = threadIdx.x >> 4;
+    const int ci = ci0 + 4 * q;
+    float4 pv[4], gv[4], vv[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int co = co0 + r * 16 + rr;
+      pv[r] = gv[r] = vv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (co < cout && ci < cin) {
+        const long long o = sg.off + ((long long)co * taps + tap) * cin + ci;
+        pv[r] = *reinterpret_cast<const float4*>(p + o); gv[r] = *reinterpret_cast<const float4*>(g + o); vv[r] = *reinterpret_cast<const float4*>(v + o);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int co = co0 + r * 16 + rr;
+      uint16_t t[4] = {0, 0, 0, 0};
+      if (co < cout && ci < cin) {
+        const long long o = sg.off + ((long long)co * taps + tap) * cin + ci;
+        sgd_update(pv[r].x, gv[r].x, vv[r].x, k); sgd_update(pv[r].y, gv[r].y, vv[r].y, k);
+        sgd_update(pv[r].z, gv[r].z, vv[r].z, k); sgd_update(pv[r].w, gv[r].w, vv[r].w, k);
+        *reinterpret_cast<float4*>(p + o) = pv[r]; *reinterpret_cast<float4*>(v + o) = vv[r];
+        const float w[4] = {pv[r].x, pv[r].y, pv[r].z, pv[r].w};
+        if (f_hi) {
+          uint16_t a[4], b[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) split_f16(w[j], a[j], b[j]);
+          const long long of = (long long)co * sg.ld_f + tap * cin + ci;
+          if ((of & 3) == 0) {
+            *reinterpret_cast<uint2*>(f_hi + of) = make_uint2(a[0] | ((uint32_t)a[1] << 16), a[2] | ((uint32_t)a[3] << 16));
+            if (f_lo) *reinterpret_cast<uint2*>(f_lo + of) = make_uint2(b[0] | ((uint32_t)b[1] << 16), b[2] | ((uint32_t)b[3] << 16));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) { f_hi[of + j] = a[j]; if (f_lo) f_lo[of + j] = b[j]; }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) t[j] = cvt_f32_to_16(w[j], sg.d_fmt);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) tile[4 * q + j][r * 16 + rr] = t[j];
+    }
+  } else {
   float pv[16], gv[16], vv[16];
   const int ci = ci0 + lane64;
 #pragma unroll
@@ -81,6 +127,7 @@ __global__ void __launch_bounds__(256) sgd_pack_kernel(const ssp_sgd_segment* __
       t = cvt_f32_to_16(w, sg.d_fmt);
     }
     tile[lane64][r * 4 + grp] = t;
+  }
   }
   if (!d) return;
   __syncthreads();
