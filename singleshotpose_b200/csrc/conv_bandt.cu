@@ -33,6 +33,7 @@ struct ConvBandTParams {
   int kc_per_tap, cin;
   int Wp, HpWp;
   int cout, stacked;
+  int ovl;                 // 32-channel 3x3 layer through the overlapping-row tensor map: a band row = [pixel | pixel + 1], K chunk 0 = taps kw 0,1, chunk 1 = tap kw 2
   uint32_t idesc;
   int stages, stage_bytes, plane_bytes, rows0, rows1;
   int w_tile_bytes, res_bytes;
@@ -93,13 +94,15 @@ __global__ void __launch_bounds__(kThreadsT, 1) conv_bandt_kernel(const __grid_c
     if (lane == 0) {
       // ---- weights: every (tap, kc) tile, once.  stacked: rows 0-63 <- W_hi, rows 64-127 <- W_lo of the same 16 KB tile ----
       const int wbox_rows = p.stacked ? 64 : p.w_tile_bytes / 128;
-      mbar_expect_tx(res_bar, (uint32_t)(p.taps * p.kc_per_tap * planes * wbox_rows * 128));
-      for (int tap = 0; tap < p.taps; tap++)
-        for (int kc = 0; kc < p.kc_per_tap; kc++) {
-          uint8_t* wt = res_base + (size_t)(tap * p.kc_per_tap + kc) * p.w_tile_bytes;
-          tma_load_2d(wt, &p.tmW[0], res_bar, tap * p.cin + kc * 64, 0);
-          if (p.stacked) tma_load_2d(wt + 64 * 128, &p.tmW[1], res_bar, tap * p.cin + kc * 64, 0);
-        }
+      mbar_expect_tx(res_bar, (uint32_t)((p.ovl ? 6 : p.taps * p.kc_per_tap) * planes * wbox_rows * 128));
+      const int ntile = p.ovl ? 6 : p.taps * p.kc_per_tap;
+      for (int ti = 0; ti < ntile; ti++) {
+        // ovl: tile 2 kh = the 64 K columns of taps (kh, 0) and (kh, 1), tile 2 kh + 1 = tap (kh, 2) (its upper 32 columns are never multiplied)
+        const int kcol = p.ovl ? (ti >> 1) * 3 * p.cin + (ti & 1) * 64 : (ti / p.kc_per_tap) * p.cin + (ti % p.kc_per_tap) * 64;
+        uint8_t* wt = res_base + (size_t)ti * p.w_tile_bytes;
+        tma_load_2d(wt, &p.tmW[0], res_bar, kcol, 0);
+        if (p.stacked) tma_load_2d(wt + 64 * 128, &p.tmW[1], res_bar, kcol, 0);
+      }
       // ---- activation bands ----
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx = (uint32_t)planes * (uint32_t)p.plane_bytes;
@@ -141,12 +144,15 @@ __global__ void __launch_bounds__(kThreadsT, 1) conv_bandt_kernel(const __grid_c
         tc_fence_after();
         const uint32_t sa = smem_u32(stage_base + (size_t)stage * p.stage_bytes);
         if (elect_one_sync()) {
-          for (int kw = 0; kw < p.nk; kw++) {
-            const uint32_t wt = rb + (uint32_t)(((kh * p.nk + kw) * p.kc_per_tap + kc) * p.w_tile_bytes);
-            const uint32_t x_hi = sa + kw * 128, x_lo = x_hi + (uint32_t)p.plane_bytes;     // tap kw starts kw rows into the band
+          const int ngrp = p.ovl ? 2 : p.nk;
+          for (int kw = 0; kw < ngrp; kw++) {
+            // ovl: group 0 = taps kw 0,1 (64 K of a [pixel | pixel + 1] row), group 1 = tap kw 2 (32 K, band read two rows further in)
+            const uint32_t wt = rb + (uint32_t)((p.ovl ? kh * 2 + kw : (kh * p.nk + kw) * p.kc_per_tap + kc) * p.w_tile_bytes);
+            const uint32_t x_hi = sa + (p.ovl ? 2 * kw : kw) * 128, x_lo = x_hi + (uint32_t)p.plane_bytes;     // tap kw starts kw rows into the band
+            const int ks = p.ovl ? (kw == 0 ? 4 : 2) : ksteps;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-              if (k < ksteps) {
+              if (k < ks) {
                 const uint64_t da = umma_desc_k_sw128(wt + k * 32);
                 if (p.stacked) { umma_f16(d_tmem, da, umma_desc_k_sw128(x_lo + k * 32), p.idesc, acc); acc = 1; }   // small terms first
                 umma_f16(d_tmem, da, umma_desc_k_sw128(x_hi + k * 32), p.idesc, acc); acc = 1;
@@ -289,9 +295,14 @@ int conv_gemm_bandt(const void* a_hi, const void* a_lo, long long a_rows, int a_
   const int planes = p.stacked ? 2 : 1;
   p.taps = taps; p.nk = taps == 9 ? 3 : 1;
   p.kc_per_tap = (cin + 63) / 64; p.cin = cin; p.cout = cout;
+  // 32-channel 3x3 layer with a row pitch of exactly 32 channels: overlapping-row tensor map (tools/probes/tmap_overlap_probe.cu) -- a band row
+  // is [pixel | pixel + 1], dense 128 B instead of 64 B + zero fill, and the taps (kh, 0), (kh, 1) share one 64-wide K chunk: six resident
+  // weight tiles instead of nine, which is what makes room for a third ring stage (block 2 forward: 477 us at 42 % tensor-active with two)
+  static const int ovl_on = []() { const char* e = getenv("SSP_BANDT_OVL"); return e ? atoi(e) : 1; }();
+  p.ovl = (ovl_on && taps == 9 && cin == 32 && a_ld == 32) ? 1 : 0;
   const int mrows = p.stacked ? 128 : ((cout + 7) / 8) * 8;
   p.w_tile_bytes = mrows * 128;
-  long long res = (long long)taps * p.kc_per_tap * p.w_tile_bytes + (128 - mrows) * 128;      // every MMA reads 128 rows from its tile's start
+  long long res = (long long)(p.ovl ? 6 : taps * p.kc_per_tap) * p.w_tile_bytes + (128 - mrows) * 128;      // every MMA reads 128 rows from its tile's start
   res = (res + 1023) / 1024 * 1024;
   const int fixed = kXchBytes + 64 + (2 * kMaxStagesT + 5) * 8 + 16 + 1024;
   int np = 0, stages = 0;
@@ -315,8 +326,9 @@ int conv_gemm_bandt(const void* a_hi, const void* a_lo, long long a_rows, int a_
   int rc = 0;
   for (int pl = 0; pl < planes; pl++) {
     const void* xa = pl ? a_lo : a_hi; const void* wa = pl ? b_lo : b_hi;
-    rc |= tmap_2d_16bit(&p.tmX[pl][0], xa, (uint64_t)cin, (uint64_t)a_rows, (uint64_t)a_ld, 64, p.rows0, a_fmt == FMT_BF16);
-    if (p.rows1) rc |= tmap_2d_16bit(&p.tmX[pl][1], xa, (uint64_t)cin, (uint64_t)a_rows, (uint64_t)a_ld, 64, p.rows1, a_fmt == FMT_BF16);
+    const uint64_t xin = p.ovl ? 64 : (uint64_t)cin, xrows = p.ovl ? (uint64_t)a_rows - 1 : (uint64_t)a_rows;
+    rc |= tmap_2d_16bit(&p.tmX[pl][0], xa, xin, xrows, (uint64_t)a_ld, 64, p.rows0, a_fmt == FMT_BF16);
+    if (p.rows1) rc |= tmap_2d_16bit(&p.tmX[pl][1], xa, xin, xrows, (uint64_t)a_ld, 64, p.rows1, a_fmt == FMT_BF16);
     rc |= tmap_2d_16bit(&p.tmW[pl], wa, (uint64_t)taps * cin, (uint64_t)b_rows, (uint64_t)b_ld, 64, p.stacked ? 64 : mrows, b_fmt == FMT_BF16);
   }
   if (rc) return fail_msg(SSP_ERR_DRIVER, "conv_gemm_bandt: cuTensorMapEncodeTiled failed");

@@ -32,6 +32,8 @@ struct WgradTcParams {
   int cout, cin, bn;
   int acc_stride;       // TMEM columns per tap accumulator (>= bn; 64 for bn = 32 so that taps merge into one N-wide MMA)
   int merge;            // taps per MMA (1 = one instruction per tap)
+  int xbox0;            // index of the first X box inside a stage: 2 (two dY boxes), or 1 when cout <= 64 (the second dY box would be all zero fill)
+  int ovl, real_taps;   // ovl: 32-channel layer through the overlapping-row tensor map -- every X box holds TWO horizontally adjacent taps (see the launcher)
   uint32_t idesc;       // N field left zero: filled per instruction
   int stages, stage_bytes;
   float* dw;
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
           if (two_dy) tma_load_2d(s + kBox, &p.tmDy, &full_bar[stage], co_t * 128 + 64, row);     // else: TMEM lanes 64-127 accumulate stale smem, never read
           for (int t = 0; t < ntap; t++)
             for (int j = 0; j < nb; j++)
-              tma_load_2d(s + (2 + t * nb + j) * kBox, &p.tmX, &full_bar[stage], ci_t * p.bn + j * 64, row + p.shifts[tap0 + t]);
+              tma_load_2d(s + (p.xbox0 + t * nb + j) * kBox, &p.tmX, &full_bar[stage], ci_t * p.bn + j * 64, row + p.shifts[tap0 + t]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
 #pragma unroll
             for (int k = 0; k < 4; k++) {   // 16 K rows per MMA = 2 swizzle groups of 8 rows = 2048 B
               const uint64_t da = umma_desc_sw128(s + k * 2048, kBox, 1024);
-              const uint64_t db = umma_desc_sw128(s + (2 + t * nb) * kBox + k * 2048, kBox, 1024);
+              const uint64_t db = umma_desc_sw128(s + (p.xbox0 + t * nb) * kBox + k * 2048, kBox, 1024);
               umma_f16(d_tmem + (uint32_t)(t * p.acc_stride), da, db, idesc, (k == 0) ? acc : 1u);
             }
           }
@@ -146,6 +148,24 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
       mbar_wait(&tfull_bar[buf], use & 1);
       tc_fence_after();
       const int co = co_t * 128 + q * 32 + lane;
+      if (p.ovl) {
+        // pseudo-tap t = kernel row t / 2, box t % 2: columns [0,32) are tap kw = 2 (t % 2), columns [32,64) tap kw + 1 (kw = 3 does not exist)
+        for (int t = 0; t < ntap; t++)
+          for (int hf = 0; hf < 2; hf++) {
+            const int kw = 2 * ((tap0 + t) & 1) + hf;
+            if (kw > 2) continue;
+            const int tap = ((tap0 + t) >> 1) * 3 + kw;
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.taps_per_group + t) * p.acc_stride + hf * 32), r);
+            tmem_ld_wait();
+            float* drow = p.dw + ((long long)co * p.real_taps + tap) * p.dw_ld;
+            if (co < p.cout && kb1 > kb0) {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (j < p.cin_store) atomicAdd(drow + j, __uint_as_float(r[j]) * p.scale);
+            }
+          }
+      } else
       for (int t = 0; t < ntap; t++) {
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.taps_per_group + t) * p.acc_stride);
         float* drow = p.dw + ((long long)co * p.taps + tap0 + t) * p.dw_ld;
@@ -193,18 +213,28 @@ int wgrad_gemm_tc(const void* dy, long long dy_rows, int dy_ld, int cout, int dy
   // sharing dY across taps pays for narrow tiles (L2-bound, deep pipeline still fits); for BN >= 128 the shallower
   // smem ring and the single TMEM buffer cost more than the saved traffic (measured), so one tap per item there
   static const int merge_on = []() { const char* e = getenv("SSP_WGRAD_MERGE"); return e ? atoi(e) : 1; }();
+  // 32-channel 3x3 layer stored with a row pitch of exactly 32 channels (block 2 of yolo-pose.cfg): a tensor map whose rows OVERLAP
+  // (inner extent 64 elements, row pitch 64 B; legal and delivered correctly, tools/probes/tmap_overlap_probe.cu) makes row r of a box
+  // the channels of pixel r followed by those of pixel r + 1, i.e. the operands of TWO horizontally adjacent taps.  Six boxes instead of
+  // nine half-empty ones, one accumulator group (384 TMEM columns) instead of two, so dY is staged once per k-block: 56 KB instead of
+  // 88-104 KB requested from L2 per 64 pixel rows (the kernel was fill-bound: 572 us at batch 64, 33 % tensor-active).
+  static const int ovl_on = []() { const char* e = getenv("SSP_WGRAD_OVL"); return e ? atoi(e) : 1; }();
+  const bool ovl = merge_on && ovl_on && taps == 9 && cin == 32 && x_ld == 32 && cin_store <= 32;
+  p.ovl = ovl ? 1 : 0; p.real_taps = taps;
+  const int ptaps = ovl ? 6 : taps;                 // ovl: six pseudo-taps = (kernel row, box 0 | 1), 64 accumulator columns each
   p.acc_stride = (merge_on && bn < 64) ? 64 : bn;
   p.merge = (merge_on && taps > 1 && p.acc_stride <= 128) ? 256 / p.acc_stride : 1;
-  int tmax = (bn <= 64) ? 512 / p.acc_stride : (p.merge > 1 ? p.merge : 1); if (tmax > taps) tmax = taps;
-  p.groups = (taps + tmax - 1) / tmax;
-  p.taps_per_group = (taps + p.groups - 1) / p.groups;
+  int tmax = (bn <= 64) ? 512 / p.acc_stride : (p.merge > 1 ? p.merge : 1); if (tmax > ptaps) tmax = ptaps;
+  p.groups = (ptaps + tmax - 1) / tmax;
+  p.taps_per_group = (ptaps + p.groups - 1) / p.groups;
   p.nbuf = (2 * p.taps_per_group * p.acc_stride <= 512) ? 2 : 1;
   p.m_rows = g.m_rows();
   p.kblocks_total = (int)((p.m_rows + 63) / 64);
   p.co_tiles = (cout + 127) / 128;
   p.ci_tiles = (cin + bn - 1) / bn;
-  p.taps = taps;
+  p.taps = ptaps;
   for (int t = 0; t < 9; t++) p.shifts[t] = (taps == 9) ? ((t / 3) - 1) * g.Wp() + ((t % 3) - 1) : 0;
+  if (ovl) for (int t = 0; t < 6; t++) p.shifts[t] = ((t / 2) - 1) * g.Wp() - 1 + 2 * (t % 2);     // box 0: taps kw = 0, 1; box 1: kw = 2 (and a non-existent kw = 3)
   p.cout = cout; p.cin = cin;
   const int base_items = p.co_tiles * p.ci_tiles * p.groups;
   // split K until there are ~2 waves of work items, keeping at least 32 k-blocks (2048 rows) per item
@@ -214,7 +244,8 @@ int wgrad_gemm_tc(const void* dy, long long dy_rows, int dy_ld, int cout, int dy
   if (splits < 1) splits = 1;
   p.splits = splits;
   p.idesc = umma_idesc_f16(dy_fmt, x_fmt, 1, 1, 0);
-  p.stage_bytes = (2 + p.taps_per_group * nb) * kBox;
+  p.xbox0 = cout > 64 ? 2 : 1;          // cout <= 64: TMEM lanes 64-127 accumulate whatever follows in the stage (the first X box); never read
+  p.stage_bytes = (p.xbox0 + p.taps_per_group * nb) * kBox;
   const int fixed = (2 * kMaxStagesW + 4) * 8 + 16 + 1024;
   int stages = (227 * 1024 - fixed) / p.stage_bytes;
   if (stages > kMaxStagesW) stages = kMaxStagesW;
@@ -222,7 +253,8 @@ int wgrad_gemm_tc(const void* dy, long long dy_rows, int dy_ld, int cout, int dy
   p.dw = dw; p.dw_ld = dw_ld; p.cin_store = cin_store; p.scale = scale;
   int rc = 0;
   rc |= tmap_2d_16bit(&p.tmDy, dy, (uint64_t)cout, (uint64_t)dy_rows, (uint64_t)dy_ld, 64, 64, dy_fmt == FMT_BF16);
-  rc |= tmap_2d_16bit(&p.tmX, x, (uint64_t)cin, (uint64_t)x_rows, (uint64_t)x_ld, 64, 64, x_fmt == FMT_BF16);
+  if (ovl) rc |= tmap_2d_16bit(&p.tmX, x, 64, (uint64_t)x_rows - 1, 32, 64, 64, x_fmt == FMT_BF16);      // overlapping rows: [pixel r | pixel r + 1]
+  else rc |= tmap_2d_16bit(&p.tmX, x, (uint64_t)cin, (uint64_t)x_rows, (uint64_t)x_ld, 64, 64, x_fmt == FMT_BF16);
   if (rc) return fail_msg(SSP_ERR_DRIVER, "wgrad_gemm_tc: cuTensorMapEncodeTiled failed");
   static int configured = 0;
   if (!configured) {
