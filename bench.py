@@ -321,6 +321,8 @@ def main():
         d[0] += flops; d[1] += a.elapsed_time(b) * 1e-3; d[2] += 1
     per_kind = {k: {"tflops": v[0] / v[1] / 1e12, "ms_per_step": 1e3 * v[1] / args.steps, "launches_per_step": v[2] // args.steps}
                 for k, v in agg.items() if v[1] > 0}
+    # kinds: "fwd" / "dgrad" / "wgrad" = the tensor-core GEMM launches of blocks 2..31; "l0_bwd" = the CUDA-core backward of blocks 0-1
+    # (csrc/l0_fused.cu: 2*N*H*W*32*27 FLOP of algebra instead of a GEMM; its forward twin is not event-timed)
     cf = agg.get("fwd", [0, 0, 0]); cd = agg.get("dgrad", [0, 0, 0])
     conv_flops, conv_t, conv_n = cf[0] + cd[0], cf[1] + cd[1], cf[2] + cd[2]
     achieved = conv_flops / conv_t / 1e12 if conv_t else 0.0

@@ -540,7 +540,7 @@ class Engine:
                     ev = torch.cuda.Event()
                     ev.record(main)
                     side.wait_event(ev)
-                self._gemm("wgrad", L, N, h, w, "ssp_l0_bwd", ptr(B.x_image), ptr(B.dx[ci]), 1 if self.dx_f16 else 0, B.dx[ci].shape[1], c0, ptr(B.l0_code), L.slope,
+                self._gemm("l0_bwd", L, N, h, w, "ssp_l0_bwd", ptr(B.x_image), ptr(B.dx[ci]), 1 if self.dx_f16 else 0, B.dx[ci].shape[1], c0, ptr(B.l0_code), L.slope,
                            N, H, W, ptr(B.l0_t1), ws, stream=wstream)
                 call("ssp_l0_bwd_finalize", ptr(B.l0_t1), ptr(B.l0_gram), ptr(self.flat_params[off:off + n]), ptr(bn.weight.data),
                      ptr(st["mean"]), ptr(st["invstd"]), float(N * h * w), inv, ptr(self.flat_grads[off:off + n]),
