@@ -281,18 +281,34 @@ def main():
     # ---------------- end-to-end timing (host buffers) ----------------
     for _ in range(2):
         run(x_host, t_host).item()
+    loss_pin = torch.empty(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    if graphed is not None:          # warm the staged path too: its copy stream, the 133 MB staging buffer and the pinned loss buffer are
+        for _ in range(2):           # created on first use and must not be billed to the timed steps (round 2: 15.06 vs 16.69 ms/step)
+            graphed.stage(x_host, t_host)
+            loss_pin[0].copy_(graphed.run_staged().detach().reshape(()), non_blocking=True)
+        torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     e0.record()
     if graphed is not None:
         # every step: pinned host -> device copy of that step's images and targets (prefetched on a copy stream so that the PCIe
         # transfer of step i+1 overlaps the replay of step i), and the loss read back to the host
+        # The loss of step i travels to a pinned host buffer right behind its replay and is READ by the host after step i+1 has been
+        # enqueued (one step of software pipelining, as a training loop that logs the loss does it): every step's loss reaches the
+        # host inside the timed region, the host's launch path no longer sits between two replays.
         graphed.stage(x_host, t_host)
+        prev = None
         for i in range(args.steps):
             l_dev = graphed.run_staged()
+            loss_pin[i & 1].copy_(l_dev.detach().reshape(()), non_blocking=True)
+            loss_ev[i & 1].record()
             if i + 1 < args.steps:
                 graphed.stage(x_host, t_host)
-            lv = l_dev.item()
+            if prev is not None:
+                loss_ev[prev].synchronize(); lv = float(loss_pin[prev])
+            prev = i & 1
+        loss_ev[prev].synchronize(); lv = float(loss_pin[prev])
     else:
         for _ in range(args.steps):
             lv = run(x_host, t_host).item()
