@@ -79,10 +79,12 @@ int ssp_conv0_direct(const float* x_nchw, const float* w, const float* bias_or_n
                      double* stat_sum_or_null, double* stat_sq_or_null, int N, int H, int W, void* stream);
 /* ---- blocks 0-1 of cfg/yolo-pose.cfg as a unit -- nn.Conv2d(3,32,3,1,1) + BatchNorm2d + LeakyReLU + MaxPool2d(2,2) (darknet.py:154-167)
  *      and their autograd (train.py:103) -- without materialising the full-resolution conv output (csrc/l0_fused.cu).
- *      gram: double[28*28] (upper triangle: sums of q q^T over all pixels, q = (27 patch values, 1)), kept from forward to backward;
+ *      gram: double[SSP_L0_GRAM_DOUBLES]; the first 28*28 hold the matrix (upper triangle: sums of q q^T over all pixels, q = (27 patch
+ *      values, 1)), kept from forward to backward; the rest is scratch of ssp_l0_gram (shift correlations, border sums);
  *      code: uint8 [pooled rows][32] (bits 0-1 arg-max position of the 2x2 window, bit 2 pre-activation > 0);
  *      t1: double[28*32] scratch (27 x 32 patch-weighted gradient sums + the 32 plain sums).  w = fp32 master weights [32][27].
  *      ssp_l0_stats writes the per-channel sum / sum of squares that ssp_bn_finalize(count = N*H*W) expects. ---- */
+#define SSP_L0_GRAM_DOUBLES 2816
 int ssp_l0_gram(const float* x_nchw, int N, int H, int W, double* gram, void* stream);
 int ssp_l0_stats(const double* gram, const float* w, double* stat_sum, double* stat_sq, void* stream);
 int ssp_l0_fused_fwd(const float* x_nchw, const float* w, const float* scale, const float* shift, float slope, int N, int H, int W,

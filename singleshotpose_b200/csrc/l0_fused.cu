@@ -132,23 +132,177 @@ __global__ void __launch_bounds__(256, 2) l0_gram_kernel(const float* __restrict
   SSP_GRAM_ROLES(SSP_GRAM_FLUSH)
 }
 
+// ------------------------------------------------------------------------------------------------ Gram matrix through shift correlations
+// The brute-force kernel above forms all 406 products of every pixel's 28-vector.  But patch entry (kh, kw, c) of output pixel p is the
+// image value x_c(u), u = p + (kh-1, kw-1), so
+//     G[(t,c),(t',c')] = sum over u in (image minus the rows / columns that tap t cannot reach) of x_c(u) * x~_c'(u + D),   D = t' - t,
+// (x~ = zero outside the image) = C[c,c',D] - Row[..] - Col[..] + Corner[..] with
+//     C[c,c',D] = sum over ALL image pixels u of x_c(u) x~_c'(u + D)      -- 25 shifts x 9 channel pairs, C[c,c',D] = C[c',c,-D]: 117 numbers
+// and the corrections sums of the same products over the first / last row and column (tap kh = 0 never reaches the last image row,
+// kh = 2 never the first; likewise kw).  l0_corr_kernel: 117 FMAs per pixel instead of 406, four pixels per lane share one 3 x 8 x 3
+// window (72 shared-memory loads per 468 FMAs); l0_border_kernel: the 8 border sets by brute force (2(H+W) pixels per image);
+// l0_gram_assemble_kernel: the 28 x 28 matrix (column 27 = sums of x, entry [27][27] = pixel count).  Round 2: 467 -> ~100 us.
+namespace {
+constexpr int kCorrN = 13 * 9 + 3;          // 13 shifts D >= 0 (lexicographic) x c x c', then the three channel sums
+constexpr int kGramScratch = 784;           // scratch behind the 28 x 28 matrix: C (117) | E[8][25][9] | T1[3] | ES1[8][3]
+constexpr int kOffC = kGramScratch, kOffE = kOffC + 117, kOffT1 = kOffE + 8 * 225, kOffES1 = kOffT1 + 3, kGramDoubles = kOffES1 + 24;
+constexpr int kCT = 32;                     // correlation tile: 32 x 32 pixels, halo 2 rows below, 2 columns left / right
+constexpr int kCW = kCT + 4, kCH = kCT + 2, kCP = 37;
+__device__ __forceinline__ int shift_index(int dh, int dw) { return dh == 0 ? dw : 3 + (dh - 1) * 5 + (dw + 2); }      // D >= 0 only
+}
+
+__global__ void __launch_bounds__(256, 1) l0_corr_kernel(const float* __restrict__ x, double* __restrict__ gram, int N, int H, int W) {
+  __shared__ float sx[3][kCH][kCP];
+  __shared__ double sacc[kCorrN];
+  for (int i = threadIdx.x; i < kCorrN; i += 256) sacc[i] = 0.0;
+  const int tiles_w = (W + kCT - 1) / kCT, tiles_h = (H + kCT - 1) / kCT;
+  const int ntiles = N * tiles_h * tiles_w;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = 4 * warp + (lane >> 3), c0 = 4 * (lane & 7);        // this lane's 4 consecutive pixels inside the tile
+  const long long HW = (long long)H * W;
+  float acc[kCorrN];
+#pragma unroll
+  for (int i = 0; i < kCorrN; i++) acc[i] = 0.f;
+  constexpr int kPer = (3 * kCH * kCW + 255) / 256;                  // halo elements per thread (15), staged one tile ahead
+  float pre[kPer];
+  auto fetch = [&](int tile) {
+    const int w0 = (tile % tiles_w) * kCT, h0 = ((tile / tiles_w) % tiles_h) * kCT, n = tile / (tiles_w * tiles_h);
+    const float* xi = x + (long long)n * 3 * HW;
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+      const int i = threadIdx.x + 256 * k;
+      const int cc = i % kCW, rr = (i / kCW) % kCH, c = i / (kCW * kCH);
+      const int hh = h0 + rr, ww = w0 + cc - 2;
+      pre[k] = (c < 3 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + c * HW + (long long)hh * W + ww) : 0.f;
+    }
+  };
+  if ((int)blockIdx.x < ntiles) fetch(blockIdx.x);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+      const int i = threadIdx.x + 256 * k;
+      const int cc = i % kCW, rr = (i / kCW) % kCH, c = i / (kCW * kCH);
+      if (c < 3) sx[c][rr][cc] = pre[k];
+    }
+    __syncthreads();
+    if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);
+    float win[3][3][8];                                              // [channel][row r0 + dh][column c0 - 2 ... c0 + 5]
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int dh = 0; dh < 3; dh++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) win[c][dh][j] = sx[c][r0 + dh][c0 + j];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float xv = win[c][0][2 + i];                           // zero for pixels of the tile that lie outside the image
+        acc[117 + c] += xv;
+#pragma unroll
+        for (int dh = 0; dh < 3; dh++)
+#pragma unroll
+          for (int dw = -2; dw <= 2; dw++) {
+            if (dh == 0 && dw < 0) continue;
+#pragma unroll
+            for (int c2 = 0; c2 < 3; c2++) {
+              const int a = shift_index(dh, dw) * 9 + c * 3 + c2;
+              acc[a] = fmaf(xv, win[c2][dh][2 + i + dw], acc[a]);
+            }
+          }
+      }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kCorrN; i++) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) atomicAdd(&sacc[i], (double)v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kCorrN; i += 256) if (sacc[i] != 0.0) atomicAdd(gram + (i < 117 ? kOffC + i : kOffT1 + (i - 117)), sacc[i]);
+}
+
+// border sets: 0 = first row, 1 = last row, 2 = first column, 3 = last column, 4..7 = corners (0,0) (0,L) (L,0) (L,L)
+__global__ void __launch_bounds__(256) l0_border_kernel(const float* __restrict__ x, double* __restrict__ gram, int N, int H, int W, int chunks) {
+  // block = (image, set, chunk of 16 border pixels); thread j < 225 = (shift D, c, c'), threads 225..227 = the plain sums of x_c.
+  // (One block per (image, set) walking all 416 pixels serially took 250 us at batch 64: a latency chain of dependent loads.)
+  constexpr int kChunk = 16;
+  const int chunk = blockIdx.x % chunks, set = (blockIdx.x / chunks) % 8, n = blockIdx.x / (chunks * 8), j = threadIdx.x;
+  if (j >= 228) return;
+  const long long HW = (long long)H * W;
+  const float* xi = x + (long long)n * 3 * HW;
+  const int npx = set < 2 ? W : (set < 4 ? H : 1);
+  const int k0 = chunk * kChunk, k1 = k0 + kChunk < npx ? k0 + kChunk : npx;
+  if (k0 >= npx) return;
+  const int di = j / 9, c = j < 225 ? (j % 9) / 3 : j - 225, c2 = j % 3;
+  const int dh = di / 5 - 2, dw = di % 5 - 2;
+  double a = 0.0;
+  for (int k = k0; k < k1; k++) {
+    int h, w;
+    if (set == 0) { h = 0; w = k; } else if (set == 1) { h = H - 1; w = k; } else if (set == 2) { h = k; w = 0; } else if (set == 3) { h = k; w = W - 1; }
+    else { h = (set & 2) ? H - 1 : 0; w = (set & 1) ? W - 1 : 0; }
+    const float xv = __ldg(xi + c * HW + (long long)h * W + w);
+    if (j >= 225) { a += (double)xv; continue; }
+    const int h2 = h + dh, w2 = w + dw;
+    if (h2 >= 0 && h2 < H && w2 >= 0 && w2 < W) a += (double)xv * (double)__ldg(xi + c2 * HW + (long long)h2 * W + w2);
+  }
+  if (a != 0.0) atomicAdd(gram + (j < 225 ? kOffE + set * 225 + j : kOffES1 + set * 3 + (j - 225)), a);
+}
+
+__global__ void l0_gram_assemble_kernel(double* __restrict__ gram, double count) {
+  for (int i = threadIdx.x; i < kG * kG; i += blockDim.x) {
+    const int a = i / kG, b = i % kG;
+    if (a > b) continue;
+    double v;
+    if (a == 27) v = count;
+    else {
+      const int ta = a / 3, c = a % 3, kh = ta / 3, kw = ta % 3;
+      const int eh = kh == 0 ? 1 : (kh == 2 ? 0 : -1), ew = kw == 0 ? 3 : (kw == 2 ? 2 : -1);      // the row / column set tap (kh, kw) never reaches
+      const int ec = (eh >= 0 && ew >= 0) ? 4 + (eh == 1 ? 2 : 0) + (ew == 3 ? 1 : 0) : -1;
+      if (b == 27) {
+        v = gram[kOffT1 + c];
+        if (eh >= 0) v -= gram[kOffES1 + eh * 3 + c];
+        if (ew >= 0) v -= gram[kOffES1 + ew * 3 + c];
+        if (ec >= 0) v += gram[kOffES1 + ec * 3 + c];
+      } else {
+        const int tb = b / 3, c2 = b % 3, dh = tb / 3 - kh, dw = tb % 3 - kw;
+        const bool pos = dh > 0 || (dh == 0 && dw >= 0);
+        v = pos ? gram[kOffC + shift_index(dh, dw) * 9 + c * 3 + c2] : gram[kOffC + shift_index(-dh, -dw) * 9 + c2 * 3 + c];
+        const int e = ((dh + 2) * 5 + (dw + 2)) * 9 + c * 3 + c2;
+        if (eh >= 0) v -= gram[kOffE + eh * 225 + e];
+        if (ew >= 0) v -= gram[kOffE + ew * 225 + e];
+        if (ec >= 0) v += gram[kOffE + ec * 225 + e];
+      }
+    }
+    gram[i] = v;
+  }
+}
+
 __device__ __forceinline__ double gram_at(const double* g, int a, int b) { return a <= b ? g[a * kG + b] : g[b * kG + a]; }
 
-// per-channel sum / sum of squares of the (never materialised) conv output from the Gram matrix: the inputs of bn_finalize
-__global__ void l0_stats_kernel(const double* __restrict__ gram, const float* __restrict__ wgt /*[32][27]*/, double* __restrict__ ssum,
-                                double* __restrict__ ssq) {
-  const int c = threadIdx.x;
-  if (c >= kC0) return;
-  double w[27];
-  for (int k = 0; k < 27; k++) w[k] = (double)wgt[c * 27 + k];
+// per-channel sum / sum of squares of the (never materialised) conv output from the Gram matrix: the inputs of bn_finalize.
+// warp = output channel, lane = Gram row (one 27-term dot product per lane, shuffle reductions; a serial 27 x 27 fp64 loop per thread
+// took 35 us of pure latency)
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__global__ void __launch_bounds__(1024) l0_stats_kernel(const double* __restrict__ gram, const float* __restrict__ wgt /*[32][27]*/,
+                                                        double* __restrict__ ssum, double* __restrict__ ssq) {
+  const int c = threadIdx.x >> 5, a = threadIdx.x & 31;
   double s = 0.0, q = 0.0;
-  for (int a = 0; a < 27; a++) {
-    s += w[a] * gram_at(gram, a, 27);
+  if (a < 27) {
+    const double wa = (double)wgt[c * 27 + a];
     double r = 0.0;
-    for (int b = 0; b < 27; b++) r += gram_at(gram, a, b) * w[b];
-    q += w[a] * r;
+    for (int b = 0; b < 27; b++) r += gram_at(gram, a, b) * (double)wgt[c * 27 + b];
+    s = wa * gram_at(gram, a, 27); q = wa * r;
   }
-  ssum[c] = s; ssq[c] = q;
+  s = warp_sum_d(s); q = warp_sum_d(q);
+  if (a == 0) { ssum[c] = s; ssq[c] = q; }
 }
 
 // ------------------------------------------------------------------------------------------------ conv + BN + leaky + 2x2 max-pool
@@ -266,15 +420,21 @@ __global__ void __launch_bounds__(256, 2) l0_bwd_kernel(const float* __restrict_
     const int hs = (t.h0 >> 1) + warp;
     const bool row_ok = 2 * hs + 1 < H;
     float gv[kTW / 2]; int cd[kTW / 2];
+    {
+      // the 16 pooled cells of a window row are consecutive rows of the pooled plane: one 64-bit row index, then pointer increments
+      const int ws0 = t.w0 >> 1;
+      const int nw = row_ok ? ((W >> 1) - ws0 < kTW / 2 ? (W >> 1) - ws0 : kTW / 2) : 0;      // windows of this row inside the image
+      const long long row0 = row_ok ? gh.row(t.n, hs, ws0) : 0;
+      const uint8_t* cp = code + row0 * kC0 + lane;
+      const __half* gp16 = reinterpret_cast<const __half*>(g) + row0 * g_ld + g_c0 + lane;
+      const float* gp32 = reinterpret_cast<const float*>(g) + row0 * g_ld + g_c0 + lane;
 #pragma unroll
-    for (int wc = 0; wc < kTW / 2; wc++) {
-      const int ws = (t.w0 >> 1) + wc;
-      const bool ok = row_ok && (2 * ws + 1 < W);
-      const long long row = ok ? gh.row(t.n, hs, ws) : 0;
-      const long long ge = row * g_ld + g_c0 + lane;
-      if (G16) gv[wc] = ok ? __half2float(__ldg(reinterpret_cast<const __half*>(g) + ge)) : 0.f;      // out-of-image windows: dz = 0
-      else gv[wc] = ok ? __ldg(reinterpret_cast<const float*>(g) + ge) : 0.f;
-      cd[wc] = ok ? (int)__ldg(code + row * kC0 + lane) : 0;
+      for (int wc = 0; wc < kTW / 2; wc++) {
+        const bool ok = wc < nw;                                          // out-of-image windows contribute dz = 0
+        if (G16) gv[wc] = ok ? __half2float(__ldg(gp16 + (long long)wc * g_ld)) : 0.f;
+        else gv[wc] = ok ? __ldg(gp32 + (long long)wc * g_ld) : 0.f;
+        cd[wc] = ok ? (int)__ldg(cp + wc * kC0) : 0;
+      }
     }
     __syncthreads();
     halo_store(sin, pre);
@@ -304,29 +464,27 @@ __global__ void __launch_bounds__(256, 2) l0_bwd_kernel(const float* __restrict_
   }
 }
 
-// dW0, dgamma, dbeta from the sums (header comment); grads are written (not accumulated), `gscale` undoes the loss scale
-__global__ void l0_bwd_finalize_kernel(const double* __restrict__ t1, const double* __restrict__ gram, const float* __restrict__ wgt,
-                                       const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
-                                       double count, float gscale, float* __restrict__ dW /*[32][27]*/, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
-  const int c = threadIdx.x;
-  if (c >= kC0) return;
-  double w[27];
-  for (int k = 0; k < 27; k++) w[k] = (double)wgt[c * 27 + k];
+// dW0, dgamma, dbeta from the sums (header comment); grads are written (not accumulated), `gscale` undoes the loss scale.
+// warp = output channel, lane = patch entry k.
+__global__ void __launch_bounds__(1024) l0_bwd_finalize_kernel(const double* __restrict__ t1, const double* __restrict__ gram, const float* __restrict__ wgt,
+                                                               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                               double count, float gscale, float* __restrict__ dW /*[32][27]*/, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta) {
+  const int c = threadIdx.x >> 5, k = threadIdx.x & 31;
   const double mu = (double)mean[c], is = (double)invstd[c], ga = (double)gamma[c];
   const double S1 = t1[27 * kC0 + c];
-  double dzy = 0.0;
-  for (int k = 0; k < 27; k++) dzy += w[k] * t1[k * kC0 + c];
+  double tk = 0.0, gw = 0.0, cs = 0.0, part = 0.0;
+  if (k < 27) {
+    tk = t1[k * kC0 + c];
+    for (int b = 0; b < 27; b++) gw += gram_at(gram, k, b) * (double)wgt[c * 27 + b];
+    cs = gram_at(gram, k, 27);
+    part = (double)wgt[c * 27 + k] * tk;
+  }
+  const double dzy = warp_sum_d(part);
   const double S2 = is * (dzy - mu * S1);
   const double k1 = S1 / count, k2 = S2 / count;
-  for (int k = 0; k < 27; k++) {
-    double gw = 0.0;
-    for (int b = 0; b < 27; b++) gw += gram_at(gram, k, b) * w[b];
-    const double cs = gram_at(gram, k, 27);
-    dW[c * 27 + k] = (float)(ga * is * (t1[k * kC0 + c] - k1 * cs - k2 * is * (gw - mu * cs)) * (double)gscale);
-  }
-  dgamma[c] = (float)(S2 * (double)gscale);
-  dbeta[c] = (float)(S1 * (double)gscale);
+  if (k < 27) dW[c * 27 + k] = (float)(ga * is * (tk - k1 * cs - k2 * is * (gw - mu * cs)) * (double)gscale);
+  if (k == 0) { dgamma[c] = (float)(S2 * (double)gscale); dbeta[c] = (float)(S1 * (double)gscale); }
 }
 
 // ================================================================================================ host launchers
@@ -342,15 +500,24 @@ int l0_gram(const float* x, int N, int H, int W, double* gram, cudaStream_t s) {
   if (!x || !gram || N <= 0 || H <= 0 || W <= 0) return fail_msg(SSP_ERR_ARG, "l0_gram: bad argument");
   const long long nt = l0_tiles(N, H, W);
   if (nt > 0x7fffffffLL) return fail_msg(SSP_ERR_ARG, "l0_gram: bad shape");
-  cudaError_t e = cudaMemsetAsync(gram, 0, sizeof(double) * kG * kG, s);
+  cudaError_t e = cudaMemsetAsync(gram, 0, sizeof(double) * kGramDoubles, s);
   if (e != cudaSuccess) return fail_cuda(e, __FILE__, __LINE__);
-  l0_gram_kernel<<<l0_grid(nt, 2), 256, 0, s>>>(x, gram, N, H, W);
+  static const int brute = []() { const char* v = getenv("SSP_L0_GRAM"); return v && v[0] == 'b'; }();      // SSP_L0_GRAM=brute: all 406 products per pixel
+  if (brute || H < 2 || W < 2) {
+    l0_gram_kernel<<<l0_grid(nt, 2), 256, 0, s>>>(x, gram, N, H, W);
+    SSP_CHECK_LAUNCH(); return SSP_OK;
+  }
+  const long long nct = (long long)N * ((H + kCT - 1) / kCT) * ((W + kCT - 1) / kCT);
+  l0_corr_kernel<<<l0_grid(nct, 1), 256, 0, s>>>(x, gram, N, H, W);
+  const int chunks = ((H > W ? H : W) + 15) / 16;
+  l0_border_kernel<<<(unsigned)(8 * N * chunks), 256, 0, s>>>(x, gram, N, H, W, chunks);
+  l0_gram_assemble_kernel<<<1, 256, 0, s>>>(gram, (double)N * H * W);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
 
 int l0_stats(const double* gram, const float* w, double* ssum, double* ssq, cudaStream_t s) {
   if (!gram || !w || !ssum || !ssq) return fail_msg(SSP_ERR_ARG, "l0_stats: bad argument");
-  l0_stats_kernel<<<1, 32, 0, s>>>(gram, w, ssum, ssq);
+  l0_stats_kernel<<<1, 1024, 0, s>>>(gram, w, ssum, ssq);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
 
@@ -382,7 +549,7 @@ int l0_bwd_finalize(const double* t1, const double* gram, const float* w, const 
                     double count, float gscale, float* dW, float* dgamma, float* dbeta, cudaStream_t s) {
   if (!t1 || !gram || !w || !gamma || !mean || !invstd || !dW || !dgamma || !dbeta || !(count > 0))
     return fail_msg(SSP_ERR_ARG, "l0_bwd_finalize: bad argument");
-  l0_bwd_finalize_kernel<<<1, 32, 0, s>>>(t1, gram, w, gamma, mean, invstd, count, gscale, dW, dgamma, dbeta);
+  l0_bwd_finalize_kernel<<<1, 1024, 0, s>>>(t1, gram, w, gamma, mean, invstd, count, gscale, dW, dgamma, dbeta);
   SSP_CHECK_LAUNCH(); return SSP_OK;
 }
 

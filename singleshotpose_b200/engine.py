@@ -147,7 +147,7 @@ class Buffers:
                 # blocks 0-1 run as one unit (csrc/l0_fused.cu): no im2col plane, no full-resolution conv output, no dY plane --
                 # the 28x28 Gram matrix of the image patches, a 1-byte code per pooled cell and 28x32 backward sums instead
                 self.x_hi.append(None); self.x_lo.append(None); self.y.append(None)
-                self.l0_gram = torch.zeros(28 * 28, dtype=torch.float64, device=dev)
+                self.l0_gram = torch.zeros(2816, dtype=torch.float64, device=dev)      # SSP_L0_GRAM_DOUBLES: the 28x28 matrix + ssp_l0_gram's scratch
                 if train:
                     self.l0_code = torch.zeros(_lib.flat_alloc_rows(N, h // 2, w // 2), 32, dtype=torch.uint8, device=dev)
                     self.l0_t1 = torch.zeros(28 * 32, dtype=torch.float64, device=dev)

@@ -438,7 +438,7 @@ def test_l0_fused_blocks_match_torch(shape):
     # ---- device
     xd = x.to(DEV)
     wm = w.permute(0, 2, 3, 1).contiguous().to(DEV)                      # master layout [co][kh][kw][ci]
-    gram = torch.zeros(28 * 28, dtype=torch.float64, device=DEV)
+    gram = torch.zeros(2816, dtype=torch.float64, device=DEV)             # SSP_L0_GRAM_DOUBLES: matrix + scratch
     ssum = torch.zeros(32, dtype=torch.float64, device=DEV); ssq = torch.zeros_like(ssum)
     s = stream_ptr()
     call("ssp_l0_gram", ptr(xd), N, H, W, ptr(gram), s)
@@ -448,7 +448,7 @@ def test_l0_fused_blocks_match_torch(shape):
     P = F.unfold(x.double(), 3, padding=1).view(N, 3, 9, H * W).permute(0, 3, 2, 1).reshape(-1, 27)      # [px][tap][c]
     Q = torch.cat([P, torch.ones(P.shape[0], 1, dtype=torch.float64)], dim=1)
     Gref = Q.t() @ Q
-    G = gram.cpu().view(28, 28)
+    G = gram.cpu()[:784].view(28, 28)
     iu = torch.triu_indices(28, 28)
     assert ((G[iu[0], iu[1]] - Gref[iu[0], iu[1]]).abs() / Gref[iu[0], iu[1]].abs().clamp_min(1.0)).max() < 2e-6
     assert (ssum.cpu() - y.detach().sum(dim=(0, 2, 3))).abs().max() < 1e-5 * cnt
