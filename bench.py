@@ -7,8 +7,8 @@ yolo-pose.cfg at 416x416, batch 64 per GPU, synthetic data, random-init weights 
 
 Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same step
 through the reference-facing API with pinned-host inputs copied H2D and the loss read back D2H every step;
-`roofline` = conv GEMM kernel (conv_tc_kernel: forward + data-gradient launches) algorithmic TFLOP/s from CUDA events
-recorded around every launch inside the timed region vs the measured bf16 GEMM peak; `cpu_baseline` = the CPU oracle
+`roofline` = the tensor-core conv GEMM kernels (conv_tc2 / conv_bandt: forward + data-gradient launches) algorithmic TFLOP/s from
+CUDA events recorded around every launch in an eager pass of the same steps vs the measured bf16 GEMM peak; `cpu_baseline` = the CPU oracle
 port (torch-CPU restatement of the reference path) timed on this box's host cores on a bounded sample.
 --impl reference times that CPU path alone (the reference has no other implementation of the hot path that runs
 without a GPU, and /root/reference is not on the GPU box).

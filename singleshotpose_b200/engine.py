@@ -461,10 +461,12 @@ class Engine:
             if L.first and self.l0_fused:
                 off, n, _gv = self._slices[id(conv.weight)]
                 w0 = ptr(self.flat_params[off:off + n])
-                if train_bn:       # batch statistics of the conv output from the Gram matrix of the image patches (no pass over y)
-                    call("ssp_l0_gram", ptr(x), N, H, W, ptr(B.l0_gram), s)
+                if train_bn or keep_for_backward:      # the Gram matrix of the image patches: batch statistics without a pass over y, and
+                    call("ssp_l0_gram", ptr(x), N, H, W, ptr(B.l0_gram), s)      # the backward's correction terms (also for a frozen-BN forward)
+                    self.launches += 3
+                if train_bn:
                     call("ssp_l0_stats", ptr(B.l0_gram), w0, ptr(st["ssum"]), ptr(st["ssq"]), s)
-                    self.launches += 2
+                    self.launches += 1
                 call("ssp_bn_finalize", ptr(st["ssum"]) if train_bn else None, ptr(st["ssq"]) if train_bn else None, float(N * h * w),
                      ptr(bn.weight.data), ptr(bn.bias.data), ptr(bn.running_mean), ptr(bn.running_var),
                      float(bn.momentum if bn.momentum is not None else 0.1), float(bn.eps), 1 if train_bn else 0,
