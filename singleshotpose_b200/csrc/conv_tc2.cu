@@ -35,6 +35,8 @@ namespace ssp {
 struct ConvTc2Params {
   CUtensorMap tmA[2];
   CUtensorMap tmB[2];     // box rows = bn / 2 (clusters of one pair) or bn / 4 (clusters of two pairs: the weight tile is multicast)
+  CUtensorMap tmAband[2]; // band mode: box {64, 136 rows}
+  int band;               // 3x3 layer with <= 64 input channels, split operands: ONE 136-row activation band per kernel row serves the three horizontal taps
   long long m_rows;       // rows of the output matrix that exist (N*(H+1)*(W+1))
   long long store_rows;   // rows that may be written (allocation bound)
   int m_tiles, n_tiles;
@@ -59,6 +61,7 @@ static constexpr int kABytes = 128 * 128;     // 128 rows x 64 x 2 B
 static constexpr int kMaxStages = 8;
 static constexpr int kAccCols = 1024;         // per-CTA statistics accumulators (channels)
 static constexpr int kThreads = 256;
+static constexpr int kBandBytes2 = 136 * 128;  // band mode: 136 activation rows (17 swizzle atoms)
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -175,7 +178,24 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(CSZ, 1, 1) conv_
         const int kb0 = ks * kblocks / p.ksplit, kb1 = (ks + 1) * kblocks / p.ksplit;
         const int nq = n0 + (int)pr * (p.bn / 4), qoff = (int)pr * (p.b_bytes / 2);      // CSZ == 4: this CTA's quarter of the weight tile
         const uint16_t bmask = (uint16_t)((1u << rank) | (1u << (rank + 2)));             // ... goes to the same half of both pairs
-        {
+        if (p.band) {
+          // per kernel row: the 136-row band [m0 + (kh-1)(W+1) - 1, +136) in both planes, then the three taps' weight tiles
+          const uint32_t txb = 2u * (uint32_t)p.stage_bytes;
+          for (int kh = 0; kh < 3; kh++) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = stage_base + (size_t)stage * p.stage_bytes;
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], txb);
+            const int arow = m0 + (kh - 1) * p.Wp - 1;
+            tma_load_2d_pair(sa, &p.tmAband[0], &full_bar[stage], 0, arow);
+            tma_load_2d_pair(sa + kBandBytes2, &p.tmAband[1], &full_bar[stage], 0, arow);
+            for (int kw = 0; kw < 3; kw++) {
+              uint8_t* sb = sa + 2 * kBandBytes2 + (size_t)kw * 2 * p.b_bytes;
+              tma_load_2d_pair(sb, &p.tmB[0], &full_bar[stage], (kh * 3 + kw) * p.cin, n0);
+              tma_load_2d_pair(sb + p.b_bytes, &p.tmB[1], &full_bar[stage], (kh * 3 + kw) * p.cin, n0);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        } else {
           for (int kb = kb0; kb < kb1; kb++) {
             const int tap = kb / p.kc_per_tap, kc = kb - tap * p.kc_per_tap;
             const int arow = m0 + p.shifts[tap];
@@ -215,6 +235,29 @@ __global__ void __launch_bounds__(kThreads, 1) __cluster_dims__(CSZ, 1, 1) conv_
         uint32_t acc = 0;
         const int ks = w % p.ksplit;
         const int nkb = (ks + 1) * kblocks / p.ksplit - ks * kblocks / p.ksplit;
+        if (p.band) {
+          const int ksteps = p.cin >= 64 ? 4 : (p.cin + 15) / 16;         // all-zero K steps (TMA zero fill) are skipped
+          for (int kh = 0; kh < 3; kh++) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(stage_base + (size_t)stage * p.stage_bytes);
+            for (int kw = 0; kw < 3; kw++) {
+              const uint32_t a_hi = sa + kw * 128, a_lo = a_hi + kBandBytes2;      // tap kw starts kw rows into the band
+              const uint32_t b_hi = sa + 2 * kBandBytes2 + (uint32_t)(kw * 2 * p.b_bytes), b_lo = b_hi + p.b_bytes;
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                if (k < ksteps) {
+                  const uint64_t dah = umma_desc_sw128(a_hi + k * 32, 16, 1024), dbh = umma_desc_sw128(b_hi + k * 32, 16, 1024);
+                  umma_f16_pair(d_tmem, umma_desc_sw128(a_lo + k * 32, 16, 1024), dbh, p.idesc, acc);  acc = 1;
+                  umma_f16_pair(d_tmem, dah, umma_desc_sw128(b_lo + k * 32, 16, 1024), p.idesc, 1);
+                  umma_f16_pair(d_tmem, dah, dbh, p.idesc, 1);
+                }
+              }
+            }
+            umma_commit_pair(&empty_bar[stage], all_mask);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        } else
         for (int kb = 0; kb < nkb; kb++) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -403,8 +446,14 @@ int conv_gemm_tc2(const void* a_hi, const void* a_lo, long long a_rows, int a_ld
   p.Wp = g.Wp(); p.HpWp = g.HpWp();
   p.cout = cout;
   p.idesc = (umma_idesc_f16(a_fmt, b_fmt, 0, 0, bn) & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24);   // M = 256
-  p.stage_bytes = (p.n_terms == 3 ? 2 : 1) * (kABytes + p.b_bytes);
+  // Band mode (round 2): 3x3, <= 64 input channels, split operands, one pair per cluster.  The per-tap kernel re-fetches the activation
+  // tile nine times (blocks 3 / 5 forward: 2.44 GB staged per launch, fill-bound at 48 % tensor-active); a 136-row band per kernel row serves the
+  // three horizontal taps through the descriptor start address (conv_band.cu's trick, here for cta_group::2): 252 KB instead of 432 KB per tile.
+  static const int band_on = []() { const char* e = getenv("SSP_TC2_BAND"); return e ? atoi(e) : 1; }();
+  p.band = (band_on && taps == 9 && cin <= 64 && p.n_terms == 3 && !fa) ? 1 : 0;
   const int fixed = 2 * kAccCols * 8 + (2 * kMaxStages + 4) * 8 + 16 + 1024;
+  if (p.band && (227 * 1024 - fixed) / (2 * kBandBytes2 + 3 * 2 * p.b_bytes) < 2) p.band = 0;      // wide N tiles: two band stages do not fit
+  p.stage_bytes = p.band ? 2 * kBandBytes2 + 3 * 2 * p.b_bytes : (p.n_terms == 3 ? 2 : 1) * (kABytes + p.b_bytes);
   int stages = (227 * 1024 - fixed) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc2: tile does not fit shared memory");
@@ -415,7 +464,11 @@ int conv_gemm_tc2(const void* a_hi, const void* a_lo, long long a_rows, int a_ld
   rc |= tmap_2d_16bit(&p.tmA[0], a_hi, (uint64_t)cin, (uint64_t)a_rows, (uint64_t)a_ld, 64, 128, a_fmt == FMT_BF16);
   // clusters of two pairs (weight tile multicast) unless switched off, a one-tile layer, or split K (its work items are not paired)
   static const int csz_env = []() { const char* e = getenv("SSP_TC2_CLUSTER"); return e ? atoi(e) : 2; }();      // 4 = opt-in (measured slower, see the kernel comment)
-  const int csz = (csz_env == 4 && p.m_tiles >= 2) ? 4 : 2;
+  const int csz = (csz_env == 4 && p.m_tiles >= 2 && !p.band) ? 4 : 2;
+  if (p.band) {
+    rc |= tmap_2d_16bit(&p.tmAband[0], a_hi, (uint64_t)cin, (uint64_t)a_rows, (uint64_t)a_ld, 64, 136, a_fmt == FMT_BF16);
+    rc |= tmap_2d_16bit(&p.tmAband[1], a_lo, (uint64_t)cin, (uint64_t)a_rows, (uint64_t)a_ld, 64, 136, a_fmt == FMT_BF16);
+  }
   const int brows = csz == 4 ? bn / 4 : bn / 2;
   rc |= tmap_2d_16bit(&p.tmB[0], b_hi, (uint64_t)taps * cin, (uint64_t)b_rows, (uint64_t)b_ld, 64, brows, b_fmt == FMT_BF16);
   if (p.n_terms == 3) {
