@@ -129,7 +129,7 @@ int conv0_direct(const float* x, const float* w, const float* bias, float* y, in
                  cudaStream_t s) {
   if (!x || !w || !y || (y_ld % 4) || y_ld < kC0 || (ssum && !ssq)) return fail_msg(SSP_ERR_ARG, "conv0_direct: bad argument");
   static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  if (!sms) sms = ssp_sm_count();
   const long long ntiles = (long long)N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
   if (ntiles <= 0 || ntiles > 0x7fffffffLL) return fail_msg(SSP_ERR_ARG, "conv0_direct: bad shape");
   long long grid = (long long)sms * 2; if (grid > ntiles) grid = ntiles;      // persistent: 2 resident blocks per SM

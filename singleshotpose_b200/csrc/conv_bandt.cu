@@ -333,7 +333,7 @@ int conv_gemm_bandt(const void* a_hi, const void* a_lo, long long a_rows, int a_
   }
   if (rc) return fail_msg(SSP_ERR_DRIVER, "conv_gemm_bandt: cuTensorMapEncodeTiled failed");
   static int sms = 0, configured = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  if (!sms) sms = ssp_sm_count();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_bandt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, __FILE__, __LINE__);

@@ -260,8 +260,7 @@ int conv_gemm_tc(const void* a_hi, const void* a_lo, long long a_rows, int a_ld,
   if (epi == EPI_BIAS && !bias) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc: bias missing");
   if (!fa && ((out_ld % 4) || ((uintptr_t)out % 16))) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc: output must be 16-B aligned with ld % 4 == 0");
   if (!g_num_sms) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    g_num_sms = ssp_sm_count();
   }
   ConvTcParams p;
   Geom g{N, H, W};

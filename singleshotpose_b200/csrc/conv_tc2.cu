@@ -420,8 +420,7 @@ int conv_gemm_tc2(const void* a_hi, const void* a_lo, long long a_rows, int a_ld
   if (!fa && epi != EPI_F16 && ((out_ld % 4) || ((uintptr_t)out % 16))) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc2: output must be 16-B aligned with ld % 4 == 0");
   if (epi == EPI_F16 && ((out_ld % 8) || ((uintptr_t)out % 16))) return fail_msg(SSP_ERR_ARG, "conv_gemm_tc2: fp16 output must be 16-B aligned with ld % 8 == 0");
   if (!g_num_sms2) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms2, cudaDevAttrMultiProcessorCount, dev);
+    g_num_sms2 = ssp_sm_count();
   }
   ConvTc2Params p;
   Geom g{N, H, W};

@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(1024) l0_bwd_finalize_kernel(const double* __r
 // ================================================================================================ host launchers
 static int l0_grid(long long ntiles, int per_sm) {
   static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  if (!sms) sms = ssp_sm_count();
   long long g = (long long)sms * per_sm;
   return (int)(g < ntiles ? g : ntiles);
 }

@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/ssp_b200.h"   // SSP_OK / SSP_ERR_* / SSP_* enums shared with the C ABI
 
@@ -26,6 +27,18 @@ namespace ssp {
 int fail_cuda(cudaError_t e, const char* file, int line);   // abi.cu: records message, returns SSP_ERR_CUDA
 int fail_msg(int code, const char* msg);
 
+// SMs the persistent kernels size their grids for.  SSP_SM_LIMIT=n (even, < the device's count) leaves SMs free, e.g. for NCCL's kernels in
+// the data-parallel step: a collective cannot co-reside with a 227-KB GEMM CTA, it needs SMs of its own to overlap with the backward pass.
+inline int ssp_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    const char* e = getenv("SSP_SM_LIMIT");
+    if (e) { const int l = atoi(e) & ~1; if (l >= 2 && l < n) n = l; }
+  }
+  return n;
+}
 enum Fmt16 { FMT_F16 = 0, FMT_BF16 = 1 };
 // GEMM epilogues: plain fp32 store | store + per-channel sum / sum-of-squares over valid pixels | + bias
 enum { EPI_F32 = 0, EPI_STATS = 1, EPI_BIAS = 2, EPI_BNACT = 4, EPI_F16 = 8 };

@@ -199,8 +199,7 @@ int wgrad_gemm_tc(const void* dy, long long dy_rows, int dy_ld, int cout, int dy
   if (!dy || !x || !dw || (taps != 1 && taps != 9)) return fail_msg(SSP_ERR_ARG, "wgrad_gemm_tc: bad argument");
   if ((dy_ld % 8) || (x_ld % 8)) return fail_msg(SSP_ERR_ARG, "wgrad_gemm_tc: leading dimensions must be multiples of 8");
   if (!g_num_sms_w) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms_w, cudaDevAttrMultiProcessorCount, dev);
+    g_num_sms_w = ssp_sm_count();
   }
   WgradTcParams p;
   Geom g{N, H, W};

@@ -215,8 +215,7 @@ int wgrad_gemm_tc2(const void* dy, long long dy_rows, int dy_ld, int cout, int d
   if ((dy_ld % 8) || (x_ld % 8)) return fail_msg(SSP_ERR_ARG, "wgrad_gemm_tc2: leading dimensions must be multiples of 8");
   if ((cout % 256) || (cin % 256)) return 1;
   if (!g_num_sms_w2) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms_w2, cudaDevAttrMultiProcessorCount, dev);
+    g_num_sms_w2 = ssp_sm_count();
   }
   WgradTc2Params p;
   Geom g{N, H, W};
